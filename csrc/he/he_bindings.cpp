@@ -1,0 +1,337 @@
+// torch.ops.hefl.* bindings for the HE core. Each op dispatches on the device of its
+// tensor arguments: CUDA tensors go to the sm_100a kernels (kernels.h), CPU tensors to the
+// host implementation (host_math.h). u64 words travel as torch.int64 (same bits).
+#include <ATen/cuda/CUDAContext.h>
+#include <torch/library.h>
+#include <torch/torch.h>
+
+#include "host_math.h"
+#include "kernels.h"
+
+namespace {
+
+using at::Tensor;
+
+inline uint64_t* u64(const Tensor& t) {
+  TORCH_CHECK(t.scalar_type() == at::kLong, "expected int64 tensor");
+  TORCH_CHECK(t.is_contiguous(), "expected contiguous tensor");
+  return reinterpret_cast<uint64_t*>(t.data_ptr<int64_t>());
+}
+inline const uint64_t* u64o(const c10::optional<Tensor>& t) {
+  return t.has_value() ? u64(*t) : nullptr;
+}
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+inline void same_device(const Tensor& a, const Tensor& b) {
+  TORCH_CHECK(a.device() == b.device(), "tensors on different devices: ", a.device(), " vs ", b.device());
+}
+
+Tensor gen_primes(int64_t bits, int64_t logn, int64_t count, at::IntArrayRef exclude) {
+  std::vector<uint64_t> ex(exclude.begin(), exclude.end());
+  auto p = hefl::host::gen_primes((int)bits, (int)logn, (int)count, ex);
+  Tensor out = at::empty({(int64_t)p.size()}, at::kLong);
+  for (size_t i = 0; i < p.size(); ++i) out.data_ptr<int64_t>()[i] = (int64_t)p[i];
+  return out;
+}
+
+std::tuple<Tensor, Tensor> build_tables(const Tensor& moduli, int64_t logn) {
+  TORCH_CHECK(moduli.is_cpu(), "moduli must be a CPU tensor");
+  const int64_t L = moduli.numel(), n = 1ll << logn;
+  Tensor tables = at::empty({L, 4, n}, at::kLong);
+  Tensor consts = at::empty({L, 8}, at::kLong);
+  hefl::host::build_tables(u64(moduli), (int)L, (int)logn, u64(tables), u64(consts));
+  return {tables, consts};
+}
+
+std::tuple<Tensor, Tensor> build_fft_tables(int64_t logn) {
+  const int64_t n = 1ll << logn;
+  Tensor rot = at::empty({n / 2}, at::kInt);
+  Tensor ksi = at::empty({2 * n + 1, 2}, at::kDouble);
+  hefl::host::build_fft_tables((int)logn, rot.data_ptr<int32_t>(), ksi.data_ptr<double>());
+  return {rot, ksi};
+}
+
+void ntt_(Tensor data, const Tensor& tables, const Tensor& consts, int64_t L, int64_t logn,
+          bool inverse) {
+  same_device(data, tables);
+  const int64_t n = 1ll << logn;
+  TORCH_CHECK(data.size(-1) == n, "last dim must be N");
+  const int64_t rows = data.numel() / n;
+  if (data.is_cuda())
+    hefl::cuda::ntt(u64(data), rows, (int)L, (int)logn, u64(tables), u64(consts), inverse, cur_stream());
+  else
+    hefl::host::ntt(u64(data), rows, (int)L, (int)logn, u64(tables), u64(consts), inverse);
+}
+
+void pointwise_(Tensor out, const Tensor& a, const c10::optional<Tensor>& b, int64_t L,
+                const Tensor& consts, int64_t op) {
+  same_device(out, a);
+  same_device(out, consts);
+  const int64_t n = a.size(-1);
+  const int64_t rows = a.numel() / n;
+  TORCH_CHECK(out.numel() == a.numel(), "out/a size mismatch");
+  int64_t brows = 1;
+  if (b.has_value()) {
+    same_device(out, *b);
+    if (op == 5) {
+      TORCH_CHECK(b->numel() >= L, "scalar vector too short");
+    } else {
+      TORCH_CHECK(b->size(-1) == n, "b last dim mismatch");
+      brows = b->numel() / n;
+      TORCH_CHECK(rows % brows == 0, "b rows must divide a rows");
+    }
+  } else {
+    TORCH_CHECK(op == 4, "b required");
+  }
+  if (out.is_cuda())
+    hefl::cuda::pointwise(u64(out), u64(a), u64o(b), rows, brows, (int)L, (int)n, u64(consts), (int)op, cur_stream());
+  else
+    hefl::host::pointwise(u64(out), u64(a), u64o(b), rows, brows, (int)L, (int)n, u64(consts), (int)op);
+}
+
+void reduce_mod_(Tensor data, int64_t L, const Tensor& consts) {
+  same_device(data, consts);
+  const int64_t n = data.size(-1);
+  const int64_t rows = data.numel() / n;
+  if (data.is_cuda())
+    hefl::cuda::reduce_mod(u64(data), rows, (int)L, (int)n, u64(consts), cur_stream());
+  else
+    hefl::host::reduce_mod(u64(data), rows, (int)L, (int)n, u64(consts));
+}
+
+Tensor ckks_encode(const Tensor& vals, int64_t C, int64_t logn, double scale, const Tensor& rot,
+                   const Tensor& ksi) {
+  same_device(vals, rot);
+  TORCH_CHECK(vals.is_contiguous(), "vals must be contiguous");
+  const int64_t n = 1ll << logn;
+  const bool f32 = vals.scalar_type() == at::kFloat;
+  TORCH_CHECK(f32 || vals.scalar_type() == at::kDouble, "vals must be float32 or float64");
+  TORCH_CHECK(vals.numel() <= C * n / 2, "too many values for C ciphertexts");
+  Tensor msg = at::empty({C, n}, vals.options().dtype(at::kLong));
+  const float* pf = f32 ? vals.data_ptr<float>() : nullptr;
+  const double* pd = f32 ? nullptr : vals.data_ptr<double>();
+  if (vals.is_cuda()) {
+    Tensor scratch;
+    double* sp = nullptr;
+    if (logn > 14) {
+      scratch = at::empty({C, n / 2, 2}, vals.options().dtype(at::kDouble));
+      sp = scratch.data_ptr<double>();
+    }
+    hefl::cuda::ckks_encode(pf, pd, C, vals.numel(), (int)logn, scale, rot.data_ptr<int32_t>(),
+                            ksi.data_ptr<double>(), msg.data_ptr<int64_t>(), sp, cur_stream());
+  } else {
+    hefl::host::ckks_encode(pf, pd, C, vals.numel(), (int)logn, scale, rot.data_ptr<int32_t>(),
+                            ksi.data_ptr<double>(), msg.data_ptr<int64_t>());
+  }
+  return msg;
+}
+
+Tensor coeff_encode(const Tensor& vals, int64_t C, int64_t n, double scale) {
+  TORCH_CHECK(vals.scalar_type() == at::kFloat && vals.is_contiguous(), "vals must be contiguous float32");
+  TORCH_CHECK(vals.numel() <= C * n, "too many values");
+  Tensor msg = at::empty({C, n}, vals.options().dtype(at::kLong));
+  if (vals.is_cuda())
+    hefl::cuda::coeff_encode(vals.data_ptr<float>(), C, vals.numel(), (int)n, scale, msg.data_ptr<int64_t>(), cur_stream());
+  else
+    hefl::host::coeff_encode(vals.data_ptr<float>(), C, vals.numel(), (int)n, scale, msg.data_ptr<int64_t>());
+  return msg;
+}
+
+Tensor crt_center(const Tensor& res, const Tensor& consts_cpu, int64_t q0_inv_q1) {
+  TORCH_CHECK(res.dim() == 3, "res must be [C,k,N]");
+  TORCH_CHECK(consts_cpu.is_cpu(), "consts_cpu must live on the CPU");
+  const int64_t C = res.size(0), k = res.size(1), n = res.size(2);
+  TORCH_CHECK(k == 1 || k == 2, "crt_center supports 1 or 2 limbs");
+  Tensor out = at::empty({C, n}, res.options().dtype(at::kDouble));
+  const uint64_t* cc = u64(consts_cpu);
+  if (res.is_cuda()) {
+    hefl::cuda::crt_center(u64(res), C, (int)k, (int)n, cc[0], k > 1 ? cc[8] : 1, k > 1 ? cc[9] : 0,
+                           k > 1 ? cc[10] : 0, (uint64_t)q0_inv_q1, out.data_ptr<double>(), cur_stream());
+  } else {
+    hefl::host::crt_center(u64(res), C, (int)k, (int)n, cc, out.data_ptr<double>());
+  }
+  return out;
+}
+
+Tensor ckks_decode(const Tensor& coeffs, int64_t logn, double inv_scale, const Tensor& rot,
+                   const Tensor& ksi, bool as_f64) {
+  same_device(coeffs, rot);
+  TORCH_CHECK(coeffs.scalar_type() == at::kDouble && coeffs.is_contiguous(), "coeffs must be contiguous float64");
+  const int64_t n = 1ll << logn;
+  const int64_t C = coeffs.numel() / n;
+  Tensor out = at::empty({C, n / 2}, coeffs.options().dtype(as_f64 ? at::kDouble : at::kFloat));
+  float* of = as_f64 ? nullptr : out.data_ptr<float>();
+  double* od = as_f64 ? out.data_ptr<double>() : nullptr;
+  if (coeffs.is_cuda()) {
+    Tensor scratch;
+    double* sp = nullptr;
+    if (logn > 14) {
+      scratch = at::empty({C, n / 2, 2}, coeffs.options());
+      sp = scratch.data_ptr<double>();
+    }
+    hefl::cuda::ckks_decode(coeffs.data_ptr<double>(), C, (int)logn, inv_scale, rot.data_ptr<int32_t>(),
+                            ksi.data_ptr<double>(), of, od, sp, cur_stream());
+  } else {
+    hefl::host::ckks_decode(coeffs.data_ptr<double>(), C, (int)logn, inv_scale, rot.data_ptr<int32_t>(),
+                            ksi.data_ptr<double>(), of, od);
+  }
+  return out;
+}
+
+// Decrypted residues [C,k,N] -> flat float32 values [nvals] (CRT + /scale + special FFT fused on GPU).
+Tensor ckks_decode_residues(const Tensor& res, const Tensor& consts_cpu, int64_t q0_inv_q1,
+                            int64_t logn, double inv_scale, const Tensor& rot, const Tensor& ksi,
+                            int64_t nvals) {
+  TORCH_CHECK(res.dim() == 3, "res must be [C,k,N]");
+  const int64_t C = res.size(0), k = res.size(1), n = res.size(2);
+  TORCH_CHECK(n == (1ll << logn), "N mismatch");
+  TORCH_CHECK(nvals <= C * n / 2, "nvals too large");
+  if (res.is_cuda()) {
+    const uint64_t* cc = u64(consts_cpu);
+    Tensor out = at::empty({nvals}, res.options().dtype(at::kFloat));
+    Tensor scratch;
+    double* sp = nullptr;
+    if (logn > 14) {
+      scratch = at::empty({C, n / 2, 2}, res.options().dtype(at::kDouble));
+      sp = scratch.data_ptr<double>();
+    }
+    hefl::cuda::ckks_decode_residues(u64(res), C, (int)k, (int)logn, cc[0], k > 1 ? cc[8] : 1,
+                                     k > 1 ? cc[9] : 0, k > 1 ? cc[10] : 0, (uint64_t)q0_inv_q1,
+                                     inv_scale, rot.data_ptr<int32_t>(), ksi.data_ptr<double>(),
+                                     out.data_ptr<float>(), nvals, sp, cur_stream());
+    return out;
+  }
+  Tensor coeffs = crt_center(res, consts_cpu, q0_inv_q1);
+  Tensor full = ckks_decode(coeffs, logn, inv_scale, rot, ksi, false);
+  return full.reshape({-1}).slice(0, 0, nvals).contiguous();
+}
+
+void encrypt_out(const c10::optional<Tensor>& msg, const Tensor& pk, int64_t C, int64_t L, int64_t logn,
+                 const Tensor& tables, const Tensor& consts, const c10::optional<Tensor>& msg_scale,
+                 int64_t seed, int64_t ct_offset, Tensor ct) {
+  same_device(pk, tables);
+  same_device(pk, ct);
+  const int64_t n = 1ll << logn;
+  TORCH_CHECK(pk.numel() == 2 * L * n, "pk must be [2,L,N]");
+  TORCH_CHECK(ct.numel() >= C * 2 * L * n, "output buffer too small");
+  const int64_t* mp = nullptr;
+  if (msg.has_value()) {
+    same_device(*msg, pk);
+    TORCH_CHECK(msg->numel() == C * n && msg->is_contiguous(), "msg must be contiguous [C,N]");
+    mp = msg->data_ptr<int64_t>();
+  }
+  if (pk.is_cuda())
+    hefl::cuda::encrypt(mp, u64(pk), u64(ct), C, (int)L, (int)logn, u64(tables), u64(consts),
+                        u64o(msg_scale), (uint64_t)seed, (uint32_t)ct_offset, cur_stream());
+  else
+    hefl::host::encrypt(mp, u64(pk), u64(ct), C, (int)L, (int)logn, u64(tables), u64(consts),
+                        u64o(msg_scale), (uint64_t)seed, (uint32_t)ct_offset);
+}
+
+Tensor encrypt(const c10::optional<Tensor>& msg, const Tensor& pk, int64_t C, int64_t L, int64_t logn,
+               const Tensor& tables, const Tensor& consts, const c10::optional<Tensor>& msg_scale,
+               int64_t seed, int64_t ct_offset) {
+  Tensor ct = at::empty({C, 2, L, 1ll << logn}, pk.options());
+  encrypt_out(msg, pk, C, L, logn, tables, consts, msg_scale, seed, ct_offset, ct);
+  return ct;
+}
+
+Tensor decrypt(const Tensor& ct, const Tensor& sk, int64_t k, int64_t logn, const Tensor& tables,
+               const Tensor& consts) {
+  same_device(ct, sk);
+  TORCH_CHECK(ct.dim() == 4 && ct.size(1) == 2, "ct must be [C,2,L,N]");
+  const int64_t C = ct.size(0), Lct = ct.size(2), n = ct.size(3);
+  TORCH_CHECK(k >= 1 && k <= Lct, "bad k");
+  Tensor out = at::empty({C, k, n}, ct.options());
+  if (ct.is_cuda())
+    hefl::cuda::decrypt(u64(ct), u64(sk), u64(out), C, (int)Lct, (int)k, (int)logn, u64(tables), u64(consts), cur_stream());
+  else
+    hefl::host::decrypt(u64(ct), u64(sk), u64(out), C, (int)Lct, (int)k, (int)logn, u64(tables), u64(consts));
+  return out;
+}
+
+Tensor keygen_secret(int64_t L, int64_t logn, const Tensor& tables, const Tensor& consts, int64_t seed) {
+  TORCH_CHECK(tables.is_cpu(), "keygen runs on the host; pass CPU tables");
+  Tensor sk = at::empty({L, 1ll << logn}, at::kLong);
+  hefl::host::sample_secret(u64(sk), (int)L, (int)logn, u64(tables), u64(consts), (uint64_t)seed);
+  return sk;
+}
+
+Tensor keygen_public(const Tensor& sk, int64_t L, int64_t logn, const Tensor& tables,
+                     const Tensor& consts, int64_t seed, int64_t idx) {
+  TORCH_CHECK(tables.is_cpu() && sk.is_cpu(), "keygen runs on the host; pass CPU tensors");
+  Tensor pk = at::empty({2, L, 1ll << logn}, at::kLong);
+  hefl::host::gen_public(u64(sk), u64(pk), (int)L, (int)logn, u64(tables), u64(consts), (uint64_t)seed, (uint32_t)idx);
+  return pk;
+}
+
+Tensor frac_encode(const Tensor& vals, int64_t n, int64_t int_digits, int64_t frac_digits) {
+  TORCH_CHECK(vals.scalar_type() == at::kDouble && vals.is_contiguous(), "vals must be contiguous float64");
+  const int64_t C = vals.numel();
+  Tensor msg = at::empty({C, n}, vals.options().dtype(at::kLong));
+  if (vals.is_cuda())
+    hefl::cuda::frac_encode(vals.data_ptr<double>(), C, (int)n, (int)int_digits, (int)frac_digits, msg.data_ptr<int64_t>(), cur_stream());
+  else
+    hefl::host::frac_encode(vals.data_ptr<double>(), C, (int)n, (int)int_digits, (int)frac_digits, msg.data_ptr<int64_t>());
+  return msg;
+}
+
+Tensor frac_decode(const Tensor& coeffs, int64_t int_digits, int64_t frac_digits) {
+  TORCH_CHECK(coeffs.scalar_type() == at::kLong && coeffs.is_contiguous() && coeffs.dim() == 2, "coeffs must be contiguous int64 [C,N]");
+  const int64_t C = coeffs.size(0), n = coeffs.size(1);
+  Tensor out = at::empty({C}, coeffs.options().dtype(at::kDouble));
+  if (coeffs.is_cuda())
+    hefl::cuda::frac_decode(coeffs.data_ptr<int64_t>(), C, (int)n, (int)int_digits, (int)frac_digits, out.data_ptr<double>(), cur_stream());
+  else
+    hefl::host::frac_decode(coeffs.data_ptr<int64_t>(), C, (int)n, (int)int_digits, (int)frac_digits, out.data_ptr<double>());
+  return out;
+}
+
+Tensor bfv_scale_round(const Tensor& x, int64_t q, int64_t p) {
+  const int64_t n = x.size(-1);
+  const int64_t C = x.numel() / n;
+  Tensor out = at::empty_like(x);
+  if (x.is_cuda())
+    hefl::cuda::bfv_scale_round(u64(x), C, (int)n, (uint64_t)q, (uint64_t)p, out.data_ptr<int64_t>(), cur_stream());
+  else
+    hefl::host::bfv_scale_round(u64(x), C, (int)n, (uint64_t)q, (uint64_t)p, out.data_ptr<int64_t>());
+  return out;
+}
+
+Tensor digit_extract(const Tensor& x, int64_t shift, int64_t bits) {
+  const int64_t n = x.size(-1);
+  const int64_t rows = x.numel() / n;
+  Tensor out = at::empty_like(x);
+  if (x.is_cuda())
+    hefl::cuda::digit_extract(u64(x), rows, (int)n, (int)shift, (int)bits, u64(out), cur_stream());
+  else
+    hefl::host::digit_extract(u64(x), rows, (int)n, (int)shift, (int)bits, u64(out));
+  return out;
+}
+
+int64_t launch_count() { return (int64_t)hefl::cuda::launch_count(); }
+
+}  // namespace
+
+TORCH_LIBRARY_FRAGMENT(hefl, m) {
+  m.def("gen_primes(int bits, int logn, int count, int[] exclude) -> Tensor", &gen_primes);
+  m.def("build_tables(Tensor moduli, int logn) -> (Tensor, Tensor)", &build_tables);
+  m.def("build_fft_tables(int logn) -> (Tensor, Tensor)", &build_fft_tables);
+  m.def("ntt_(Tensor(a!) data, Tensor tables, Tensor consts, int L, int logn, bool inverse) -> ()", &ntt_);
+  m.def("pointwise_(Tensor(a!) out, Tensor a, Tensor? b, int L, Tensor consts, int op) -> ()", &pointwise_);
+  m.def("reduce_mod_(Tensor(a!) data, int L, Tensor consts) -> ()", &reduce_mod_);
+  m.def("ckks_encode(Tensor vals, int C, int logn, float scale, Tensor rot, Tensor ksi) -> Tensor", &ckks_encode);
+  m.def("coeff_encode(Tensor vals, int C, int n, float scale) -> Tensor", &coeff_encode);
+  m.def("crt_center(Tensor res, Tensor consts_cpu, int q0_inv_q1) -> Tensor", &crt_center);
+  m.def("ckks_decode(Tensor coeffs, int logn, float inv_scale, Tensor rot, Tensor ksi, bool as_f64) -> Tensor", &ckks_decode);
+  m.def("ckks_decode_residues(Tensor res, Tensor consts_cpu, int q0_inv_q1, int logn, float inv_scale, Tensor rot, Tensor ksi, int nvals) -> Tensor", &ckks_decode_residues);
+  m.def("encrypt(Tensor? msg, Tensor pk, int C, int L, int logn, Tensor tables, Tensor consts, Tensor? msg_scale, int seed, int ct_offset) -> Tensor", &encrypt);
+  m.def("encrypt_out(Tensor? msg, Tensor pk, int C, int L, int logn, Tensor tables, Tensor consts, Tensor? msg_scale, int seed, int ct_offset, Tensor(a!) out) -> ()", &encrypt_out);
+  m.def("decrypt(Tensor ct, Tensor sk, int k, int logn, Tensor tables, Tensor consts) -> Tensor", &decrypt);
+  m.def("keygen_secret(int L, int logn, Tensor tables, Tensor consts, int seed) -> Tensor", &keygen_secret);
+  m.def("keygen_public(Tensor sk, int L, int logn, Tensor tables, Tensor consts, int seed, int idx) -> Tensor", &keygen_public);
+  m.def("frac_encode(Tensor vals, int n, int int_digits, int frac_digits) -> Tensor", &frac_encode);
+  m.def("frac_decode(Tensor coeffs, int int_digits, int frac_digits) -> Tensor", &frac_decode);
+  m.def("bfv_scale_round(Tensor x, int q, int p) -> Tensor", &bfv_scale_round);
+  m.def("digit_extract(Tensor x, int shift, int bits) -> Tensor", &digit_extract);
+  m.def("launch_count() -> int", &launch_count);
+}

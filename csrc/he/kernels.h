@@ -1,0 +1,54 @@
+// Launchers of the sm_100a HE kernels (csrc/he/cuda/he_kernels.cu). Plain C++
+// signatures with raw device pointers so the .cu files compile without the
+// PyTorch headers (seconds, not minutes); csrc/bindings.cpp adapts tensors.
+//
+// Layouts: ciphertext batch [C][2][L][N] u64 in NTT form; plaintext/message
+// [C][N]; tables [L][4][N]; consts [L][8] (see host_math.h).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace hefl {
+namespace cuda {
+
+void ntt(uint64_t* data, int64_t rows, int L, int logn, const uint64_t* tables,
+         const uint64_t* consts, bool inverse, cudaStream_t st);
+void pointwise(uint64_t* out, const uint64_t* a, const uint64_t* b, int64_t rows, int64_t brows,
+               int L, int n, const uint64_t* consts, int op, cudaStream_t st);
+void reduce_mod(uint64_t* data, int64_t rows, int L, int n, const uint64_t* consts,
+                cudaStream_t st);
+void ckks_encode(const float* vals_f32, const double* vals_f64, int64_t C, int64_t nvals_total,
+                 int logn, double scale, const int32_t* rot_group, const double* ksi, int64_t* msg,
+                 double* scratch, cudaStream_t st);
+void ckks_decode_residues(const uint64_t* res, int64_t C, int k, int logn, uint64_t q0, uint64_t q1,
+                          uint64_t q1_ratio_lo, uint64_t q1_ratio_hi, uint64_t q0_inv_q1,
+                          double inv_scale, const int32_t* rot_group, const double* ksi,
+                          float* out, int64_t nvals_total, double* scratch, cudaStream_t st);
+void ckks_decode(const double* coeffs, int64_t C, int logn, double inv_scale,
+                 const int32_t* rot_group, const double* ksi, float* out_f32, double* out_f64,
+                 double* scratch, cudaStream_t st);
+void coeff_encode(const float* vals, int64_t C, int64_t nvals_total, int n, double scale,
+                  int64_t* msg, cudaStream_t st);
+void encrypt(const int64_t* msg, const uint64_t* pk, uint64_t* ct, int64_t C, int L, int logn,
+             const uint64_t* tables, const uint64_t* consts, const uint64_t* msg_scale,
+             uint64_t seed, uint32_t ct_offset, cudaStream_t st);
+void decrypt(const uint64_t* ct, const uint64_t* sk, uint64_t* out, int64_t C, int Lct, int k,
+             int logn, const uint64_t* tables, const uint64_t* consts, cudaStream_t st);
+void crt_center(const uint64_t* res, int64_t C, int k, int n, uint64_t q0, uint64_t q1,
+                uint64_t q1_ratio_lo, uint64_t q1_ratio_hi, uint64_t q0_inv_q1, double* out,
+                cudaStream_t st);
+void frac_encode(const double* vals, int64_t C, int n, int int_digits, int frac_digits,
+                 int64_t* msg, cudaStream_t st);
+void frac_decode(const int64_t* coeffs, int64_t C, int n, int int_digits, int frac_digits,
+                 double* out, cudaStream_t st);
+void bfv_scale_round(const uint64_t* x, int64_t C, int n, uint64_t q, uint64_t p, int64_t* out,
+                     cudaStream_t st);
+void digit_extract(const uint64_t* x, int64_t rows, int n, int shift, int bits, uint64_t* out,
+                   cudaStream_t st);
+
+// Number of kernels launched by this library since process start (bench.py's gpu_launches).
+uint64_t launch_count();
+void note_launch(uint64_t n = 1);
+
+}  // namespace cuda
+}  // namespace hefl

@@ -1,0 +1,173 @@
+"""GPU tests: every sm_100a HE kernel against its host C++ twin (bit-exact for integer
+kernels) and the CKKS pipeline end to end. Run on the B200 box: pytest -m gpu."""
+import pytest
+import torch
+
+from hefl_b200 import _ext
+from hefl_b200.he.context import CKKSContext
+
+pytestmark = pytest.mark.gpu
+ops = _ext.ops()
+
+
+def _ctx_pair(n, bits, scale_bits=40):
+    c = CKKSContext(n, prime_bits=bits, scale_bits=scale_bits, enforce_security=False)
+    g = CKKSContext(n, primes=c.primes, scale_bits=scale_bits, enforce_security=False, device="cuda")
+    return c, g
+
+
+@pytest.mark.parametrize("logn,bits", [(10, (27,)), (12, (36, 36, 37)), (13, (54, 54, 54, 55)),
+                                       (14, (60, 59, 58)), (15, (60, 60))])
+def test_ntt_gpu_matches_cpu(logn, bits):
+    n = 1 << logn
+    c, g = _ctx_pair(n, bits)
+    L = len(bits)
+    gen = torch.Generator().manual_seed(logn)
+    a = torch.stack([torch.randint(0, q, (5, n), generator=gen, dtype=torch.int64) for q in c.primes], dim=1).contiguous()
+    ref = a.clone()
+    ops.ntt_(ref, c.tables, c.consts, L, logn, False)
+    x = a.cuda()
+    ops.ntt_(x, g.tables, g.consts, L, logn, False)
+    assert torch.equal(x.cpu(), ref)
+    ops.ntt_(x, g.tables, g.consts, L, logn, True)
+    assert torch.equal(x.cpu(), a)
+
+
+def test_pointwise_and_reduce_gpu_match_cpu():
+    c, g = _ctx_pair(4096, (36, 36, 37))
+    gen = torch.Generator().manual_seed(0)
+    a = torch.stack([torch.randint(0, q, (4, 2, 4096), generator=gen, dtype=torch.int64) for q in c.primes], dim=2).contiguous()
+    b = torch.stack([torch.randint(0, q, (2, 4096), generator=gen, dtype=torch.int64) for q in c.primes], dim=1).contiguous()
+    for op in (0, 1, 2, 3):
+        ref = a.clone()
+        ops.pointwise_(ref, a, b, 3, c.consts, op)
+        out = a.clone().cuda()
+        ops.pointwise_(out, a.cuda(), b.cuda(), 3, g.consts, op)
+        assert torch.equal(out.cpu(), ref), op
+    big = torch.randint(-2**63, 2**63 - 1, (6, 4096), generator=gen, dtype=torch.int64)
+    ref = big.clone()
+    ops.reduce_mod_(ref, 3, c.consts)
+    out = big.cuda()
+    ops.reduce_mod_(out, 3, g.consts)
+    assert torch.equal(out.cpu(), ref)
+
+
+@pytest.mark.parametrize("n,bits", [(4096, (36, 36, 37)), (8192, (54, 54, 54, 55)), (16384, (54, 54, 54, 54)),
+                                    (32768, (60, 60))])
+def test_encrypt_decrypt_gpu_bit_exact_vs_cpu(n, bits):
+    c, g = _ctx_pair(n, bits)
+    sk, pk = c.keygen(seed=5)
+    gen = torch.Generator().manual_seed(1)
+    vals = torch.randn(n + 100, generator=gen)
+    msg = c.encode(vals)
+    msg_g = g.encode(vals.cuda())
+    assert (msg_g.cpu() - msg).abs().max() <= 1  # fp64 FFT: rounding may differ by one unit
+    L = len(bits)
+    ct_c = ops.encrypt(msg, pk, msg.shape[0], L, c.logn, c.tables, c.consts, None, 77, 3)
+    ct_g = ops.encrypt(msg.cuda(), pk.cuda(), msg.shape[0], L, g.logn, g.tables, g.consts, None, 77, 3)
+    assert torch.equal(ct_g.cpu(), ct_c)
+    res_c = ops.decrypt(ct_c, sk, min(L, 2), c.logn, c.tables, c.consts)
+    res_g = ops.decrypt(ct_g, sk.cuda(), min(L, 2), g.logn, g.tables, g.consts)
+    assert torch.equal(res_g.cpu(), res_c)
+    cc = ops.crt_center(res_c, c.consts_cpu, c.q0_inv_q1)
+    cg = ops.crt_center(res_g, g.consts_cpu, g.q0_inv_q1)
+    assert torch.equal(cg.cpu(), cc)
+
+
+def test_fedavg_end_to_end_on_gpu():
+    g = CKKSContext(4096, prime_bits=(36, 36, 37), scale_bits=40, device="cuda")
+    sk, pk = g.keygen(seed=9)
+    gen = torch.Generator().manual_seed(2)
+    K = 8
+    ws = [torch.randn(222722, generator=gen).cuda() * 0.05 for _ in range(K)]
+    cts = [g.encrypt(w, pk, seed=10 + i) for i, w in enumerate(ws)]
+    assert cts[0].count == 109
+    agg = g.sum_batches(cts)
+    out = g.decrypt(agg, sk, divide_by=K)
+    ref = torch.stack(ws).mean(0)
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max() < 1e-6
+
+
+def test_coeff_packing_and_scalar_mul_gpu():
+    g = CKKSContext(4096, prime_bits=(36, 36, 37), scale_bits=40, device="cuda")
+    sk, pk = g.keygen(seed=4)
+    vals = torch.linspace(-2, 2, 6000).cuda()
+    ct = g.encrypt(vals, pk, seed=9, packing="coeff")
+    out = g.decrypt(ct, sk)
+    assert (out - vals).abs().max() < 1e-6
+    ct2 = g.encrypt(vals[:2048], pk, seed=10)
+    g.mul_scalar_(ct2, 0.125)
+    assert (g.decrypt(ct2, sk) - vals[:2048] * 0.125).abs().max() < 1e-4
+
+
+def test_ct_ct_multiply_gpu():
+    g = CKKSContext(4096, prime_bits=(36, 36, 37), scale_bits=40, device="cuda")
+    sk, pk = g.keygen(seed=8)
+    rlk = g.relin_keygen(sk, seed=8, digit_bits=12)
+    a = torch.linspace(-1, 1, 2048).cuda()
+    b = torch.linspace(0.5, 1.5, 2048).cuda()
+    prod = g.multiply(g.encrypt(a, pk, seed=14), g.encrypt(b, pk, seed=15), rlk)
+    assert (g.decrypt(prod, sk) - a * b).abs().max() < 5e-3
+
+
+def test_local_sum_modq_gpu_matches_cpu():
+    c, g = _ctx_pair(4096, (36, 36, 37))
+    gen = torch.Generator().manual_seed(3)
+    srcs = [torch.stack([torch.randint(0, q, (3, 2, 4096), generator=gen, dtype=torch.int64) for q in c.primes], dim=2).contiguous()
+            for _ in range(5)]
+    ref = torch.empty_like(srcs[0])
+    ops.local_sum_modq(srcs, ref, 3, 12, c.consts)
+    exp = sum(s.clone() for s in srcs)
+    for l, q in enumerate(c.primes):
+        assert torch.equal(ref[:, :, l], exp[:, :, l] % q)
+    out = torch.empty_like(srcs[0]).cuda()
+    ops.local_sum_modq([s.cuda() for s in srcs], out, 3, 12, g.consts)
+    assert torch.equal(out.cpu(), ref)
+
+
+@pytest.mark.parametrize("world,algo", [(1, 0), (1, 1), (2, 0), (2, 1), (4, 0), (4, 1)])
+def test_fused_allreduce_protocol_single_gpu(world, algo):
+    """The multi-rank flag protocol exercised on ONE GPU: `world` logical ranks with their own
+    buffers and signal pads run the kernel concurrently on separate streams."""
+    c, g = _ctx_pair(4096, (36, 36, 37))
+    gen = torch.Generator().manual_seed(world * 10 + algo)
+    shape = (7, 2, 3, 4096)
+    numel = 7 * 2 * 3 * 4096
+    inputs = [torch.stack([torch.randint(0, q, (7, 2, 4096), generator=gen, dtype=torch.int64) for q in c.primes], dim=2).contiguous()
+              for _ in range(world)]
+    exp = sum(x.clone() for x in inputs)
+    for l, q in enumerate(c.primes):
+        exp[:, :, l] %= q
+    bufs = [x.cuda().reshape(-1).clone() for x in inputs]
+    blocks = 4
+    sigs = [torch.zeros(2 * blocks * world + 64, dtype=torch.int32, device="cuda") for _ in range(world)]
+    outs = [torch.zeros(numel, dtype=torch.int64, device="cuda") for _ in range(world)]
+    status = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(world)]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    torch.cuda.synchronize()
+    for r in range(world):
+        with torch.cuda.stream(streams[r]):
+            ops.allreduce_modq([b.data_ptr() for b in bufs], [s.data_ptr() for s in sigs], 0,
+                               outs[r] if algo == 1 else None, status[r], g.consts_cpu, numel, 3, 12,
+                               r, world, algo, blocks, 256, 3000)
+    torch.cuda.synchronize()
+    for r in range(world):
+        assert int(status[r].item()) == 0
+        got = (outs[r] if algo == 1 else bufs[r]).view(shape).cpu()
+        assert torch.equal(got, exp), (r, algo)
+        assert int(sigs[r].abs().sum().item()) == 0  # flags returned to rest
+
+
+def test_fused_allreduce_timeout_is_detected():
+    """Fault injection: a 2-rank launch where rank 1 never shows up must time out, not hang."""
+    c, g = _ctx_pair(4096, (36,))
+    numel = 2 * 4096
+    buf = torch.zeros(numel, dtype=torch.int64, device="cuda")
+    sig = torch.zeros(256, dtype=torch.int32, device="cuda")
+    sig_peer = torch.ones(256, dtype=torch.int32, device="cuda")  # peer pad never drains
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops.allreduce_modq([buf.data_ptr(), buf.data_ptr()], [sig.data_ptr(), sig_peer.data_ptr()], 0, None,
+                       status, g.consts_cpu, numel, 1, 12, 0, 2, 0, 2, 64, 50)
+    torch.cuda.synchronize()
+    assert int(status.item()) != 0

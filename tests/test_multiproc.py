@@ -1,0 +1,37 @@
+"""Multi-process tests. CPU (gloo, world 2) checks the host-side transport logic here;
+the GPU variants run the fused NVLink kernel across real devices on the B200 box."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WORKER = os.path.join(ROOT, "tests", "mp_allreduce_worker.py")
+
+
+def _run(nproc, backend, port, extra=()):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER, "--backend", backend, *extra]
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("MP_REPORT ")][-1]
+    return json.loads(line[len("MP_REPORT "):])
+
+
+def test_collective_transport_gloo_world2():
+    rep = _run(2, "gloo", 29611, ["--rounds", "2", "--cts", "3"])
+    assert rep["world"] == 2 and rep["checks"] == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.multigpu
+@pytest.mark.parametrize("nproc", [2, 4, 8])
+def test_fused_allreduce_across_gpus(nproc):
+    if torch.cuda.device_count() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    rep = _run(nproc, "nccl", 29620 + nproc)
+    assert rep["world"] == nproc and rep["checks"] >= 5 + 2 * 6

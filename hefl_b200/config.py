@@ -31,7 +31,7 @@ HE_PRESETS = {
     "n16384_l8": dict(n=16384, prime_bits=(54,) * 8, scale_bits=40),
     "n16384_l4": dict(n=16384, prime_bits=(54,) * 4, scale_bits=40),
     # CPU plumbing config
-    "n2048_l1": dict(n=2048, prime_bits=(54,), scale_bits=26),
+    "n2048_l1": dict(n=2048, prime_bits=(54,), scale_bits=40),
 }
 
 

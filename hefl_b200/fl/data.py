@@ -1,0 +1,191 @@
+"""Data pipeline (FLPyfhelin.py:38-114).
+
+* ``prep_df`` scans ``folder/<label>/<file>`` exactly like the reference (:38-55).
+* ``SyntheticImageDataset`` stands in for the medical image folders (no dataset offline):
+  uint8 NHWC images in pinned host memory with a label-dependent pattern so that training
+  has signal.
+* ``shard_range`` is the reference's IID contiguous shard (:75-78, remainder dropped, Q9);
+  ``split_train_val`` is Keras' ``validation_split=0.1`` (:85 — the first 10 % validate).
+* ``BatchFeeder`` streams batches host->device from pinned memory on a copy stream
+  (double-buffered), which is what the end-to-end benchmark times.
+"""
+from __future__ import annotations
+
+import os
+from typing import Iterator, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+
+def prep_df(folder: str, shuffle: bool = True, seed: Optional[int] = None):
+    """DataFrame ['Path','Label'] of absolute paths, optionally shuffled (FLPyfhelin.py:38-55)."""
+    import pandas as pd
+
+    rows = []
+    for sub in os.scandir(folder):
+        if sub.is_dir():
+            for name in sorted(os.listdir(sub.path)):
+                rows.append([os.path.join(os.path.abspath(sub.path), name), sub.name])
+    df = pd.DataFrame(rows, columns=["Path", "Label"])
+    if shuffle:
+        df = df.sample(frac=1, random_state=seed).reset_index(drop=True)
+    return df
+
+
+def shard_range(total: int, index: int, num_client: int) -> Tuple[int, int]:
+    ratio = int(total / num_client)
+    start = index * ratio
+    return start, start + ratio
+
+
+def split_train_val(start: int, end: int, val_frac: float = 0.1) -> Tuple[range, range]:
+    n = end - start
+    nval = int(n * val_frac)
+    return range(start + nval, end), range(start, start + nval)
+
+
+class SyntheticImageDataset:
+    """``n`` uint8 images [n, H, W, C] (pinned when CUDA is present) and int64 labels."""
+
+    def __init__(self, n: int, image_size: int = 256, channels: int = 3, classes: int = 2,
+                 seed: int = 0, pin: Optional[bool] = None):
+        g = torch.Generator().manual_seed(seed)
+        self.labels = torch.randint(0, classes, (n,), generator=g)
+        base = torch.randint(0, 160, (n, image_size, image_size, channels), generator=g, dtype=torch.uint8)
+        # class signal: a bright square whose position depends on the label
+        q = max(2, image_size // 4)
+        for c in range(classes):
+            idx = (self.labels == c).nonzero().flatten()
+            if idx.numel() == 0:
+                continue
+            r0 = (c * q) % max(1, image_size - q)
+            base[idx, r0:r0 + q, r0:r0 + q, :] += 90
+        self.images = base
+        pin = torch.cuda.is_available() if pin is None else pin
+        if pin:
+            self.images = self.images.pin_memory()
+            self.labels = self.labels.pin_memory()
+        self.n = n
+        self.classes = classes
+
+    def __len__(self) -> int:
+        return self.n
+
+
+class BatchFeeder:
+    """Fixed-size batches over an index range. On CUDA every step's images go host->device
+    straight from the pinned dataset (one async copy per row, issued by the native
+    ``gather_h2d_`` op on a copy stream) while the previous batch computes."""
+
+    def __init__(self, ds: SyntheticImageDataset, indices: range, batch_size: int, device: torch.device,
+                 shuffle: bool = True, seed: int = 0, drop_last: bool = False):
+        from .. import _ext
+
+        self.ops = _ext.ops()
+        self.ds = ds
+        self.indices = torch.tensor(list(indices), dtype=torch.int64)
+        self.bs = batch_size
+        self.device = device
+        self.shuffle = shuffle
+        self.gen = torch.Generator().manual_seed(seed)
+        self.cuda = device.type == "cuda"
+        self.copy_stream = torch.cuda.Stream(device) if self.cuda else None
+        n = len(self.indices)
+        self.steps = n // batch_size if drop_last else (n + batch_size - 1) // batch_size
+        shp = (batch_size, *ds.images.shape[1:])
+        self._stage_y = [torch.empty(batch_size, dtype=torch.int64).pin_memory() if self.cuda
+                         else torch.empty(batch_size, dtype=torch.int64) for _ in range(2)]
+        self._dev_x = [torch.empty(shp, dtype=torch.uint8, device=device) for _ in range(2)]
+        self._dev_y = [torch.empty(batch_size, dtype=torch.int64, device=device) for _ in range(2)]
+        self._ready = [torch.cuda.Event() if self.cuda else None for _ in range(2)]
+        self._consumed = [torch.cuda.Event() if self.cuda else None for _ in range(2)]
+        self.bytes_per_step = int(np.prod(shp)) + batch_size * 8
+
+    def _order(self) -> torch.Tensor:
+        if self.shuffle:
+            return self.indices[torch.randperm(len(self.indices), generator=self.gen)]
+        return self.indices
+
+    def _issue(self, order: torch.Tensor, step: int, slot: int) -> None:
+        n = len(order)
+        sel = order[(torch.arange(self.bs) + step * self.bs) % n]  # wrap the last partial batch
+        if not self.cuda:
+            self._dev_x[slot].copy_(self.ds.images[sel])
+            self._dev_y[slot].copy_(self.ds.labels[sel])
+            return
+        if step >= 2:
+            self._ready[slot].synchronize()          # pinned label staging of this slot is free again
+        torch.index_select(self.ds.labels, 0, sel, out=self._stage_y[slot])
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self._consumed[slot])
+            self.ops.gather_h2d_(self._dev_x[slot], self.ds.images, sel)
+            self._dev_y[slot].copy_(self._stage_y[slot], non_blocking=True)
+            self._ready[slot].record(self.copy_stream)
+
+    def epoch(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+        """Yields device tensors (uint8 NHWC images, int64 labels); batch i+1 copies while i computes."""
+        order = self._order()
+        if self.cuda:
+            cur = torch.cuda.current_stream(self.device)
+            for ev in self._consumed:
+                ev.record(cur)
+        self._issue(order, 0, 0)
+        for step in range(self.steps):
+            slot = step & 1
+            if step + 1 < self.steps:
+                self._issue(order, step + 1, 1 - slot)
+            if self.cuda:
+                torch.cuda.current_stream(self.device).wait_event(self._ready[slot])
+            yield self._dev_x[slot], self._dev_y[slot]
+            if self.cuda:
+                self._consumed[slot].record(torch.cuda.current_stream(self.device))
+
+
+def augment_batch(x: torch.Tensor, gen: Optional[torch.Generator], shear: float = 0.2, zoom: float = 0.2,
+                  hflip: bool = True) -> torch.Tensor:
+    """Keras ImageDataGenerator(shear_range, zoom_range, horizontal_flip) on the device
+    (FLPyfhelin.py:80-86). ``x`` is float [B,C,H,W]; one random affine per sample."""
+    import math
+
+    B = x.shape[0]
+    dev = x.device
+    r = torch.rand(B, 4, generator=gen, device=dev)
+    sh = (r[:, 0] * 2 - 1) * shear * (math.pi / 180.0)   # Keras shear_range is in degrees
+    zx = 1.0 + (r[:, 1] * 2 - 1) * zoom
+    zy = 1.0 + (r[:, 2] * 2 - 1) * zoom
+    flip = torch.where(r[:, 3] < 0.5, -1.0, 1.0) if hflip else torch.ones(B, device=dev)
+    theta = torch.zeros(B, 2, 3, device=dev, dtype=x.dtype)
+    theta[:, 0, 0] = (zx * flip).to(x.dtype)
+    theta[:, 0, 1] = (-torch.sin(sh) * zx).to(x.dtype)
+    theta[:, 1, 1] = (torch.cos(sh) * zy).to(x.dtype)
+    grid = torch.nn.functional.affine_grid(theta, list(x.shape), align_corners=False)
+    return torch.nn.functional.grid_sample(x, grid, mode="bilinear", padding_mode="border", align_corners=False)
+
+
+class ResidentFeeder:
+    """Device-resident variant of ``BatchFeeder`` (the whole shard lives in HBM; batches are
+    gathered on the device). Used for the device-only timing pass of bench.py; the shard
+    (>= 126 MB for the reference shape) is larger than L2, so no batch is served from cache."""
+
+    def __init__(self, ds: SyntheticImageDataset, indices: range, batch_size: int, device: torch.device,
+                 shuffle: bool = True, seed: int = 0):
+        idx = torch.tensor(list(indices), dtype=torch.int64)
+        self.images = ds.images[idx].to(device)
+        self.labels = ds.labels[idx].to(device)
+        self.bs = batch_size
+        self.device = device
+        self.shuffle = shuffle
+        self.gen = torch.Generator(device=device).manual_seed(seed) if device.type == "cuda" else torch.Generator().manual_seed(seed)
+        n = len(idx)
+        self.n = n
+        self.steps = (n + batch_size - 1) // batch_size
+        self.bytes_per_step = 0
+
+    def epoch(self):
+        n = self.n
+        order = torch.randperm(n, generator=self.gen, device=self.device) if self.shuffle else torch.arange(n, device=self.device)
+        ar = torch.arange(self.bs, device=self.device)
+        for step in range(self.steps):
+            sel = order[(ar + step * self.bs) % n]
+            yield self.images[sel], self.labels[sel]

@@ -1,0 +1,238 @@
+"""Local (per-client) training: the PyTorch replacement of ``model.fit`` in the reference
+(FLPyfhelin.py:161-198).
+
+Recipe kept from the reference: Adam(lr=1e-3) with Keras' legacy time-based decay 1e-4 (:140),
+categorical cross-entropy + accuracy (:141), batch 32 (:33), EarlyStopping on training loss
+(patience 5, restore best weights, :186), ReduceLROnPlateau on training loss (patience 2,
+factor 0.3, floor 1e-6, :187), ModelCheckpoint on best training accuracy (:189-191),
+augmentation shear/zoom/flip and 1/255 rescale (:80-86).
+
+B200 design: parameters, gradients and Adam moments are flat fp32 buffers (``ParamPack``),
+the optimiser is one fused kernel, the whole step (preprocess -> forward -> backward -> Adam)
+is captured in a CUDA graph and replayed, the learning-rate scale and step counter live on
+the device, and losses are read back asynchronously (one sync per epoch, not per step).
+Two NN backends: ``cudnn`` (PyTorch autograd + cuDNN/cuBLAS in bf16 autocast — the baseline)
+and ``tcgen05`` (hand-written implicit-GEMM kernels, ``hefl_b200.ops.conv``).
+"""
+from __future__ import annotations
+
+import dataclasses
+import os
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from .. import _ext
+from ..config import FLConfig
+from ..models.pack import ParamPack
+from .data import BatchFeeder, augment_batch
+
+
+@dataclasses.dataclass
+class EpochStats:
+    loss: float
+    accuracy: float
+    val_loss: float
+    val_accuracy: float
+    lr_scale: float
+
+
+class LocalTrainer:
+    def __init__(self, model: torch.nn.Module, pack: ParamPack, cfg: FLConfig, device: torch.device,
+                 backend: Optional[str] = None, augment: bool = True, use_graph: Optional[bool] = None):
+        self.ops = _ext.ops()
+        self.model = model
+        self.pack = pack
+        self.cfg = cfg
+        self.device = device
+        self.backend = backend or cfg.nn_backend
+        self.augment = augment
+        self.cuda = device.type == "cuda"
+        self.use_graph = self.cuda if use_graph is None else (use_graph and self.cuda)
+        n = pack.n_trainable
+        self.m = torch.zeros(n, dtype=torch.float32, device=device)
+        self.v = torch.zeros(n, dtype=torch.float32, device=device)
+        self.step_t = torch.zeros(1, dtype=torch.int64, device=device)
+        self.lr_scale = torch.ones(1, dtype=torch.float32, device=device)
+        self.amp_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[cfg.dtype]
+        B, S, C = cfg.batch_size, cfg.image_size, cfg.in_channels
+        self.static_x = torch.zeros(B, S, S, C, dtype=torch.uint8, device=device)
+        self.static_y = torch.zeros(B, dtype=torch.int64, device=device)
+        self.out_train = torch.zeros(2, dtype=torch.float32, device=device)   # loss, ncorrect
+        self.out_eval = torch.zeros(2, dtype=torch.float32, device=device)
+        self._graph_train: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_eval: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_launches = [0, 0]      # our kernels inside one train / eval graph
+        self.replayed_launches = 0        # ... summed over replays (bench.py gpu_launches)
+        self.engine = None
+        if self.backend == "tcgen05":
+            from ..ops.conv_engine import MedCNNEngine
+
+            self.engine = MedCNNEngine(model, pack, cfg, device)
+
+    # ------------------------------------------------------------------ one step (eager)
+    def _prep(self, x_u8: torch.Tensor, train: bool) -> torch.Tensor:
+        x = x_u8.permute(0, 3, 1, 2).to(torch.float32) * (1.0 / 255.0)   # NHWC storage, NCHW view
+        if train and self.augment:
+            x = augment_batch(x, None)
+        return x
+
+    def _forward(self, x_u8: torch.Tensor, train: bool) -> torch.Tensor:
+        x = self._prep(x_u8, train)
+        if self.amp_dtype != torch.float32 and self.cuda:
+            with torch.autocast("cuda", dtype=self.amp_dtype):
+                return self.model(x).float()
+        return self.model(x)
+
+    def _train_eager(self, x_u8: torch.Tensor, y: torch.Tensor) -> None:
+        if self.engine is not None:
+            self.engine.train_step(x_u8, y, self.out_train, augment=self.augment)
+        else:
+            logits = self._forward(x_u8, True)
+            loss = F.cross_entropy(logits, y)
+            loss.backward()
+            self.out_train[0] = loss.detach()
+            self.out_train[1] = (logits.argmax(1) == y).sum()
+        self.step_t += 1
+        c = self.cfg
+        self.ops.adam_step_(self.pack.trainable(), self.pack.grad, self.m, self.v,
+                            self.engine.shadow if self.engine is not None else None,
+                            self.step_t, self.lr_scale, c.lr, c.lr_decay, 0.9, 0.999, 1e-7)
+        if self.engine is not None:
+            self.engine.after_update()
+
+    def _eval_eager(self, x_u8: torch.Tensor, y: torch.Tensor) -> None:
+        with torch.no_grad():
+            if self.engine is not None:
+                self.engine.eval_step(x_u8, y, self.out_eval)
+                return
+            logits = self._forward(x_u8, False)
+            self.out_eval[0] = F.cross_entropy(logits, y)
+            self.out_eval[1] = (logits.argmax(1) == y).sum()
+
+    # ------------------------------------------------------------------ graph capture
+    def _capture(self) -> None:
+        self.model.train()
+        snap = (self.pack.flat.clone(), self.m.clone(), self.v.clone(), self.step_t.clone())
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._train_eager(self.static_x, self.static_y)
+                self._eval_eager(self.static_x, self.static_y)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        l0 = int(self.ops.launch_count())
+        self._graph_train = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph_train):
+            self._train_eager(self.static_x, self.static_y)
+        l1 = int(self.ops.launch_count())
+        self._graph_eval = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph_eval):
+            self._eval_eager(self.static_x, self.static_y)
+        self.graph_launches = [l1 - l0, int(self.ops.launch_count()) - l1]
+        # undo the warm-up updates
+        self.pack.flat.copy_(snap[0]); self.m.copy_(snap[1]); self.v.copy_(snap[2]); self.step_t.copy_(snap[3])
+        self.pack.grad.zero_()
+        if self.engine is not None:
+            self.engine.after_restore()
+        torch.cuda.synchronize(self.device)
+
+    # ------------------------------------------------------------------ public API
+    def train_step(self, x_u8: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """One optimisation step on a uint8 NHWC batch. Returns a device tensor [loss, ncorrect]."""
+        if self.use_graph:
+            if self._graph_train is None:
+                self._capture()
+            self.static_x.copy_(x_u8, non_blocking=True)
+            self.static_y.copy_(y, non_blocking=True)
+            self._graph_train.replay()
+            self.replayed_launches += self.graph_launches[0]
+        else:
+            self._train_eager(x_u8, y)
+        return self.out_train
+
+    def eval_step(self, x_u8: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        if self.use_graph:
+            if self._graph_eval is None:
+                self._capture()
+            self.static_x.copy_(x_u8, non_blocking=True)
+            self.static_y.copy_(y, non_blocking=True)
+            self._graph_eval.replay()
+            self.replayed_launches += self.graph_launches[1]
+        else:
+            self._eval_eager(x_u8, y)
+        return self.out_eval
+
+    def fit(self, train: BatchFeeder, val: Optional[BatchFeeder], epochs: int,
+            early_stopping: Optional[int] = 5, restore_best: bool = True,
+            reduce_lr_patience: Optional[int] = 2, reduce_lr_factor: float = 0.3, min_lr: float = 1e-6,
+            checkpoint_path: Optional[str] = None,
+            on_epoch: Optional[Callable[[int, EpochStats], None]] = None) -> List[EpochStats]:
+        """The reference's ``model.fit(train_ds, validation_data=val_ds, callbacks=[checkpoint,
+        early, lr_red], epochs=epoch)`` (FLPyfhelin.py:193)."""
+        hist: List[EpochStats] = []
+        best_loss, best_acc, wait_es, wait_lr = float("inf"), -1.0, 0, 0
+        best_weights = None
+        B = self.cfg.batch_size
+        pinned = self.cuda
+        for ep in range(epochs):
+            self.model.train()
+            ts = torch.zeros(train.steps, 2, dtype=torch.float32)
+            ts = ts.pin_memory() if pinned else ts
+            for i, (x, y) in enumerate(train.epoch()):
+                out = self.train_step(x, y)
+                ts[i].copy_(out, non_blocking=True)       # D2H of the step's loss/accuracy
+            vs = None
+            if val is not None and val.steps > 0:
+                self.model.eval()
+                vs = torch.zeros(val.steps, 2, dtype=torch.float32)
+                vs = vs.pin_memory() if pinned else vs
+                for i, (x, y) in enumerate(val.epoch()):
+                    out = self.eval_step(x, y)
+                    vs[i].copy_(out, non_blocking=True)
+            if self.cuda:
+                torch.cuda.current_stream(self.device).synchronize()
+            loss = float(ts[:, 0].mean())
+            acc = float(ts[:, 1].sum()) / (train.steps * B)
+            vloss = float(vs[:, 0].mean()) if vs is not None else float("nan")
+            vacc = float(vs[:, 1].sum()) / (val.steps * B) if vs is not None else float("nan")
+            st = EpochStats(loss, acc, vloss, vacc, float(self.lr_scale.item()))
+            hist.append(st)
+            if on_epoch:
+                on_epoch(ep, st)
+            # ModelCheckpoint(monitor='accuracy', save_best_only=True)
+            if checkpoint_path and acc > best_acc:
+                torch.save({"flat": self.pack.flat.detach().cpu(), "epoch": ep, "accuracy": acc}, checkpoint_path)
+            best_acc = max(best_acc, acc)
+            # ReduceLROnPlateau(monitor='loss') and EarlyStopping(monitor='loss')
+            if loss < best_loss:
+                best_loss, wait_es, wait_lr = loss, 0, 0
+                if early_stopping is not None and restore_best:
+                    best_weights = self.pack.flat.clone()
+            else:
+                wait_es += 1
+                wait_lr += 1
+                if reduce_lr_patience is not None and wait_lr >= reduce_lr_patience:
+                    cur = float(self.lr_scale.item()) * self.cfg.lr
+                    new = max(cur * reduce_lr_factor, min_lr)
+                    self.lr_scale.fill_(new / self.cfg.lr)
+                    wait_lr = 0
+                if early_stopping is not None and wait_es >= early_stopping:
+                    if restore_best and best_weights is not None:
+                        self.pack.flat.copy_(best_weights)
+                        if self.engine is not None:
+                            self.engine.after_restore()
+                    break
+        return hist
+
+    def reset_optimizer(self) -> None:
+        self.m.zero_(); self.v.zero_(); self.step_t.zero_(); self.lr_scale.fill_(1.0)
+        self.pack.grad.zero_()
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return {"m": self.m.cpu(), "v": self.v.cpu(), "step": self.step_t.cpu(), "lr_scale": self.lr_scale.cpu()}
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.step_t.copy_(sd["step"]); self.lr_scale.copy_(sd["lr_scale"])

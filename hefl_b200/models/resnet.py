@@ -1,0 +1,102 @@
+"""ResNet-18 / ResNet-50 (BASELINE.json configs[2], configs[4]) written against plain
+torch.nn so there is no torchvision dependency. BatchNorm running statistics are part of the
+federated state (Keras ``get_weights`` includes moving mean/variance, FLPyfhelin.py:151)."""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple, Type
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, cin: int, planes: int, stride: int = 1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, planes, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.down = None
+        if stride != 1 or cin != planes:
+            self.down = nn.Sequential(nn.Conv2d(cin, planes, 1, stride, bias=False), nn.BatchNorm2d(planes))
+
+    def forward(self, x):
+        idt = x if self.down is None else self.down(x)
+        out = F.relu(self.bn1(self.conv1(x)))
+        out = self.bn2(self.conv2(out))
+        return F.relu(out + idt)
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, cin: int, planes: int, stride: int = 1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.down = None
+        if stride != 1 or cin != planes * 4:
+            self.down = nn.Sequential(nn.Conv2d(cin, planes * 4, 1, stride, bias=False), nn.BatchNorm2d(planes * 4))
+
+    def forward(self, x):
+        idt = x if self.down is None else self.down(x)
+        out = F.relu(self.bn1(self.conv1(x)))
+        out = F.relu(self.bn2(self.conv2(out)))
+        out = self.bn3(self.conv3(out))
+        return F.relu(out + idt)
+
+
+class ResNet(nn.Module):
+    def __init__(self, block: Type[nn.Module], layers: Tuple[int, ...], num_classes: int = 1000,
+                 in_channels: int = 3):
+        super().__init__()
+        self.in_channels = in_channels
+        self.num_classes = num_classes
+        self.conv1 = nn.Conv2d(in_channels, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        cin = 64
+        stages = []
+        for i, (planes, n) in enumerate(zip((64, 128, 256, 512), layers)):
+            blocks = []
+            for j in range(n):
+                blocks.append(block(cin, planes, stride=2 if (j == 0 and i > 0) else 1))
+                cin = planes * block.expansion
+            stages.append(nn.Sequential(*blocks))
+        self.stages = nn.Sequential(*stages)
+        self.fc = nn.Linear(cin, num_classes)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+
+    def forward(self, x):
+        x = F.max_pool2d(F.relu(self.bn1(self.conv1(x))), 3, 2, 1)
+        x = self.stages(x)
+        x = F.adaptive_avg_pool2d(x, 1).flatten(1)
+        return self.fc(x)
+
+    def keras_layers(self) -> List[Tuple[str, Optional[nn.Module]]]:
+        """One entry per weight-bearing module, in definition order."""
+        out: List[Tuple[str, Optional[nn.Module]]] = []
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                out.append(("conv", m))
+            elif isinstance(m, nn.BatchNorm2d):
+                out.append(("bn", m))
+            elif isinstance(m, nn.Linear):
+                out.append(("dense", m))
+        return out
+
+
+def resnet18(num_classes: int = 1000, in_channels: int = 3) -> ResNet:
+    return ResNet(BasicBlock, (2, 2, 2, 2), num_classes, in_channels)
+
+
+def resnet50(num_classes: int = 1000, in_channels: int = 3) -> ResNet:
+    return ResNet(Bottleneck, (3, 4, 6, 3), num_classes, in_channels)

@@ -13,5 +13,26 @@ void adam_step(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_
                const int64_t* step, const float* lr_scale, float lr, float decay, float beta1,
                float beta2, float eps, cudaStream_t st);
 
+// ---- tcgen05 implicit-GEMM convolution (conv_tcgen05.cu) ----
+void conv_fwd_pool(const void* X, const void* Wf, const float* bias, void* out, uint8_t* argmax, int B, int H,
+                   int W, int CK, int CO, cudaStream_t st);
+void conv_dgrad(const void* dY, const void* Wd, void* dX, int B, int H, int W, int CK, int CO, cudaStream_t st);
+void conv_wgrad(const void* X, const void* DY, float* dW32, int P, int W, int CK, int Co, cudaStream_t st);
+
+// ---- data-movement kernels around the convolutions (nn_kernels.cu) ----
+constexpr int kMaxConvLayers = 8;
+struct ConvLayerTable {
+  int n;
+  int Ci[kMaxConvLayers], CK[kMaxConvLayers], Co[kMaxConvLayers];
+  int64_t w_off[kMaxConvLayers], b_off[kMaxConvLayers];       // offsets into the flat fp32 parameter buffer
+  int64_t wf_off[kMaxConvLayers], wd_off[kMaxConvLayers];     // offsets (elements) into the bf16 Wf / Wd buffers
+  int64_t dw_off[kMaxConvLayers];                             // offsets (elements) into the fp32 dW32 buffer
+};
+void preprocess_u8(const uint8_t* x, const float* theta, void* X, int B, int H, int W, cudaStream_t st);
+void unpool_relu(const void* g, const uint8_t* amax, const void* ypool, void* dY, int B, int H, int W, int Hp,
+                 int Wp, int Co, cudaStream_t st);
+void conv_weight_relayout(const void* shadow, const ConvLayerTable& t, void* Wf, void* Wd, cudaStream_t st);
+void conv_grad_finalize(float* dW32, const ConvLayerTable& t, float* grad, cudaStream_t st);
+
 }  // namespace nn
 }  // namespace hefl

@@ -71,9 +71,101 @@ void gather_h2d_(Tensor dst, const Tensor& src, const Tensor& indices) {
   }
 }
 
+inline cudaStream_t cur() { return at::cuda::getCurrentCUDAStream().stream(); }
+inline void chk_bf16(const Tensor& t, const char* n) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kBFloat16 && t.is_contiguous(), n, " must be a contiguous CUDA bf16 tensor");
+}
+
+void conv_fwd_pool(const Tensor& X, const Tensor& Wf, const Tensor& bias, Tensor out,
+                   const c10::optional<Tensor>& argmax, int64_t B, int64_t H, int64_t W, int64_t CK, int64_t CO) {
+  chk_bf16(X, "X"); chk_bf16(Wf, "Wf"); chk_bf16(out, "out");
+  TORCH_CHECK(X.numel() == B * H * W * CK, "X must be [B*H*W, CK]");
+  TORCH_CHECK(Wf.numel() == 9 * CO * CK, "Wf must be [9, CO, CK]");
+  TORCH_CHECK(bias.is_cuda() && bias.scalar_type() == at::kFloat && bias.numel() == CO, "bias must be float32 [CO]");
+  const int64_t Hp = (H - 2) / 2, Wp = (W - 2) / 2;
+  TORCH_CHECK(out.numel() == B * Hp * Wp * CO, "out must be [B,Hp,Wp,CO]");
+  uint8_t* am = nullptr;
+  if (argmax.has_value()) {
+    TORCH_CHECK(argmax->scalar_type() == at::kByte && argmax->numel() == out.numel(), "bad argmax");
+    am = argmax->data_ptr<uint8_t>();
+  }
+  hefl::nn::conv_fwd_pool(X.data_ptr(), Wf.data_ptr(), bias.data_ptr<float>(), out.data_ptr(), am, (int)B, (int)H,
+                          (int)W, (int)CK, (int)CO, cur());
+}
+
+void conv_dgrad(const Tensor& dY, const Tensor& Wd, Tensor dX, int64_t B, int64_t H, int64_t W, int64_t CK,
+                int64_t CO) {
+  chk_bf16(dY, "dY"); chk_bf16(Wd, "Wd"); chk_bf16(dX, "dX");
+  TORCH_CHECK(dY.numel() == B * H * W * CK && dX.numel() == B * H * W * CO && Wd.numel() == 9 * CO * CK, "shape mismatch");
+  hefl::nn::conv_dgrad(dY.data_ptr(), Wd.data_ptr(), dX.data_ptr(), (int)B, (int)H, (int)W, (int)CK, (int)CO, cur());
+}
+
+void conv_wgrad(const Tensor& X, const Tensor& DY, Tensor dW32, int64_t P, int64_t W, int64_t CK, int64_t Co) {
+  chk_bf16(X, "X"); chk_bf16(DY, "DY");
+  TORCH_CHECK(X.numel() == P * CK && DY.numel() == P * Co, "X must be [P,CK] and DY [P,Co]");
+  TORCH_CHECK(dW32.is_cuda() && dW32.scalar_type() == at::kFloat && dW32.numel() >= (9 * CK + 1) * Co, "dW32 too small");
+  hefl::nn::conv_wgrad(X.data_ptr(), DY.data_ptr(), dW32.data_ptr<float>(), (int)P, (int)W, (int)CK, (int)Co, cur());
+}
+
+void preprocess_u8(const Tensor& x, const c10::optional<Tensor>& theta, Tensor X) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kByte && x.is_contiguous() && x.dim() == 4 && x.size(3) == 3, "x must be uint8 [B,H,W,3]");
+  chk_bf16(X, "X");
+  const int64_t B = x.size(0), H = x.size(1), W = x.size(2);
+  TORCH_CHECK(X.numel() == B * H * W * 16, "X must be [B*H*W, 16]");
+  const float* th = nullptr;
+  if (theta.has_value()) {
+    TORCH_CHECK(theta->is_cuda() && theta->scalar_type() == at::kFloat && theta->numel() == B * 6 && theta->is_contiguous(), "theta must be float32 [B,2,3]");
+    th = theta->data_ptr<float>();
+  }
+  hefl::nn::preprocess_u8(x.data_ptr<uint8_t>(), th, X.data_ptr(), (int)B, (int)H, (int)W, cur());
+}
+
+void unpool_relu(const Tensor& g, const Tensor& amax, const Tensor& ypool, Tensor dY, int64_t B, int64_t H,
+                 int64_t W, int64_t Co) {
+  chk_bf16(g, "g"); chk_bf16(ypool, "ypool"); chk_bf16(dY, "dY");
+  const int64_t Hp = (H - 2) / 2, Wp = (W - 2) / 2;
+  TORCH_CHECK(g.numel() == B * Hp * Wp * Co && ypool.numel() == g.numel() && amax.numel() == g.numel(), "pooled shapes mismatch");
+  TORCH_CHECK(amax.scalar_type() == at::kByte, "amax must be uint8");
+  TORCH_CHECK(dY.numel() == B * H * W * Co, "dY must be [B*H*W, Co]");
+  TORCH_CHECK(Co % 8 == 0, "Co must be a multiple of 8");
+  hefl::nn::unpool_relu(g.data_ptr(), amax.data_ptr<uint8_t>(), ypool.data_ptr(), dY.data_ptr(), (int)B, (int)H,
+                        (int)W, (int)Hp, (int)Wp, (int)Co, cur());
+}
+
+hefl::nn::ConvLayerTable table_from(const Tensor& t) {
+  TORCH_CHECK(t.is_cpu() && t.scalar_type() == at::kLong && t.dim() == 2 && t.size(1) == 8, "table must be CPU int64 [n,8]");
+  hefl::nn::ConvLayerTable T;
+  T.n = (int)t.size(0);
+  TORCH_CHECK(T.n <= hefl::nn::kMaxConvLayers, "too many conv layers");
+  const int64_t* p = t.data_ptr<int64_t>();
+  for (int l = 0; l < T.n; ++l) {
+    T.Ci[l] = (int)p[l * 8 + 0]; T.CK[l] = (int)p[l * 8 + 1]; T.Co[l] = (int)p[l * 8 + 2];
+    T.w_off[l] = p[l * 8 + 3]; T.b_off[l] = p[l * 8 + 4]; T.wf_off[l] = p[l * 8 + 5];
+    T.wd_off[l] = p[l * 8 + 6]; T.dw_off[l] = p[l * 8 + 7];
+  }
+  return T;
+}
+
+void conv_weight_relayout(const Tensor& shadow, const Tensor& table, Tensor Wf, Tensor Wd) {
+  chk_bf16(shadow, "shadow"); chk_bf16(Wf, "Wf"); chk_bf16(Wd, "Wd");
+  hefl::nn::conv_weight_relayout(shadow.data_ptr(), table_from(table), Wf.data_ptr(), Wd.data_ptr(), cur());
+}
+
+void conv_grad_finalize(Tensor dW32, const Tensor& table, Tensor grad) {
+  TORCH_CHECK(dW32.is_cuda() && dW32.scalar_type() == at::kFloat && grad.is_cuda() && grad.scalar_type() == at::kFloat, "float32 CUDA tensors required");
+  hefl::nn::conv_grad_finalize(dW32.data_ptr<float>(), table_from(table), grad.data_ptr<float>(), cur());
+}
+
 }  // namespace
 
 TORCH_LIBRARY_FRAGMENT(hefl, m) {
   m.def("adam_step_(Tensor(a!) p, Tensor(b!) g, Tensor(c!) m, Tensor(d!) v, Tensor? shadow, Tensor step, Tensor? lr_scale, float lr, float decay, float beta1, float beta2, float eps) -> ()", &adam_step_);
   m.def("gather_h2d_(Tensor(a!) dst, Tensor src, Tensor indices) -> ()", &gather_h2d_);
+  m.def("conv_fwd_pool(Tensor X, Tensor Wf, Tensor bias, Tensor(a!) out, Tensor(b!)? argmax, int B, int H, int W, int CK, int CO) -> ()", &conv_fwd_pool);
+  m.def("conv_dgrad(Tensor dY, Tensor Wd, Tensor(a!) dX, int B, int H, int W, int CK, int CO) -> ()", &conv_dgrad);
+  m.def("conv_wgrad(Tensor X, Tensor DY, Tensor(a!) dW32, int P, int W, int CK, int Co) -> ()", &conv_wgrad);
+  m.def("preprocess_u8(Tensor x, Tensor? theta, Tensor(a!) X) -> ()", &preprocess_u8);
+  m.def("unpool_relu(Tensor g, Tensor amax, Tensor ypool, Tensor(a!) dY, int B, int H, int W, int Co) -> ()", &unpool_relu);
+  m.def("conv_weight_relayout(Tensor shadow, Tensor table, Tensor(a!) Wf, Tensor(b!) Wd) -> ()", &conv_weight_relayout);
+  m.def("conv_grad_finalize(Tensor(a!) dW32, Tensor table, Tensor(b!) grad) -> ()", &conv_grad_finalize);
 }

@@ -44,3 +44,175 @@ void adam_step(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_
 
 }  // namespace nn
 }  // namespace hefl
+
+// ------------------------------------------------------------------------------------------
+// Data-movement kernels around the tcgen05 convolutions
+// ------------------------------------------------------------------------------------------
+namespace hefl {
+namespace nn {
+
+// uint8 NHWC (3 channels) -> bf16 [P,16] (channels 3..15 zero), with 1/255 rescale and an optional per-sample affine warp (Keras shear/zoom/flip,
+// FLPyfhelin.py:80-86) sampled bilinearly with border clamp (torch.grid_sample semantics,
+// align_corners=False).
+__global__ void preprocess_u8_kernel(const uint8_t* __restrict__ x, const float* __restrict__ theta,
+                                     __nv_bfloat16* __restrict__ X, int B, int H, int W) {
+  const int64_t P = (int64_t)B * H * W;
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < P; m += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(m % W);
+    const int h = (int)((m / W) % H);
+    const int b = (int)(m / ((int64_t)W * H));
+    float c[3];
+    if (theta) {
+      const float* t = theta + b * 6;
+      const float xn = (2.f * w + 1.f) / W - 1.f, yn = (2.f * h + 1.f) / H - 1.f;
+      const float sx = t[0] * xn + t[1] * yn + t[2], sy = t[3] * xn + t[4] * yn + t[5];
+      float ix = ((sx + 1.f) * W - 1.f) * 0.5f, iy = ((sy + 1.f) * H - 1.f) * 0.5f;
+      ix = fminf(fmaxf(ix, 0.f), (float)(W - 1));
+      iy = fminf(fmaxf(iy, 0.f), (float)(H - 1));
+      const int x0 = (int)floorf(ix), y0 = (int)floorf(iy);
+      const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+      const float fx = ix - x0, fy = iy - y0;
+      const uint8_t* img = x + (int64_t)b * H * W * 3;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float v00 = img[((int64_t)y0 * W + x0) * 3 + k], v01 = img[((int64_t)y0 * W + x1) * 3 + k];
+        const float v10 = img[((int64_t)y1 * W + x0) * 3 + k], v11 = img[((int64_t)y1 * W + x1) * 3 + k];
+        c[k] = ((v00 * (1.f - fx) + v01 * fx) * (1.f - fy) + (v10 * (1.f - fx) + v11 * fx) * fy) * (1.f / 255.f);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) c[k] = (float)x[m * 3 + k] * (1.f / 255.f);
+    }
+    const uint32_t b0 = __bfloat16_as_ushort(__float2bfloat16(c[0]));
+    const uint32_t b1 = __bfloat16_as_ushort(__float2bfloat16(c[1]));
+    const uint32_t b2 = __bfloat16_as_ushort(__float2bfloat16(c[2]));
+    uint4* dst = reinterpret_cast<uint4*>(X + m * 16);
+    dst[0] = make_uint4(b0 | (b1 << 16), b2, 0u, 0u);
+    dst[1] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+void preprocess_u8(const uint8_t* x, const float* theta, void* X, int B, int H, int W, cudaStream_t st) {
+  const int64_t P = (int64_t)B * H * W;
+  int blocks = (int)((P + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  preprocess_u8_kernel<<<blocks, 256, 0, st>>>(x, theta, reinterpret_cast<__nv_bfloat16*>(X), B, H, W);
+  hefl::cuda::note_launch();
+}
+
+// Gradient of (ReLU -> 2x2 max-pool): scatter the pooled gradient to the arg-max position on the
+// conv-input grid, zero elsewhere (including the invalid border). Output [P, Co] bf16 feeds both
+// dgrad (K-major A operand) and wgrad (MN-major B operand). One thread = one pixel x 8 channels.
+__global__ void unpool_relu_kernel(const __nv_bfloat16* __restrict__ g, const uint8_t* __restrict__ amax,
+                                   const __nv_bfloat16* __restrict__ ypool, __nv_bfloat16* __restrict__ dY, int B,
+                                   int H, int W, int Hp, int Wp, int Co) {
+  const int64_t P = (int64_t)B * H * W;
+  const int groups = Co >> 3;
+  const int64_t total = P * groups;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = t / groups;
+    const int cg = (int)(t % groups);
+    const int w = (int)(m % W);
+    const int h = (int)((m / W) % H);
+    const int b = (int)(m / ((int64_t)W * H));
+    const int hp = h >> 1, wp = w >> 1;
+    uint4 outv = make_uint4(0u, 0u, 0u, 0u);
+    if (hp < Hp && wp < Wp) {
+      const int64_t o = (((int64_t)b * Hp + hp) * Wp + wp) * Co + cg * 8;
+      const uint4 gv = *reinterpret_cast<const uint4*>(g + o);
+      const uint4 yv = *reinterpret_cast<const uint4*>(ypool + o);
+      const uint2 av = *reinterpret_cast<const uint2*>(amax + o);
+      const uint32_t pos = (uint32_t)((h & 1) * 2 + (w & 1));
+      const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+      const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
+      const uint32_t aw[2] = {av.x, av.y};
+      uint32_t ow[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t r = 0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c = i * 2 + j;
+          const uint32_t a8 = (aw[c >> 2] >> ((c & 3) * 8)) & 0xFFu;
+          const uint32_t yb = (yw[i] >> (16 * j)) & 0xFFFFu;
+          const bool on = a8 == pos && yb != 0u && (yb & 0x8000u) == 0u;   // pooled > 0
+          if (on) r |= ((gw[i] >> (16 * j)) & 0xFFFFu) << (16 * j);
+        }
+        ow[i] = r;
+      }
+      outv = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+    *reinterpret_cast<uint4*>(dY + m * Co + cg * 8) = outv;
+  }
+}
+
+void unpool_relu(const void* g, const uint8_t* amax, const void* ypool, void* dY, int B, int H, int W, int Hp,
+                 int Wp, int Co, cudaStream_t st) {
+  const int64_t total = (int64_t)B * H * W * (Co / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  unpool_relu_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), amax,
+                                             reinterpret_cast<const __nv_bfloat16*>(ypool),
+                                             reinterpret_cast<__nv_bfloat16*>(dY), B, H, W, Hp, Wp, Co);
+  hefl::cuda::note_launch();
+}
+
+// bf16 shadow of the flat parameters ([Co][Ci][3][3] per conv) -> Wf [tap][Co][CK] (forward B
+// operand, channel-padded) and Wd [tap][Ci][Co] (dgrad B operand).
+__global__ void conv_weight_relayout_kernel(const __nv_bfloat16* __restrict__ shadow, const ConvLayerTable t,
+                                            __nv_bfloat16* __restrict__ Wf, __nv_bfloat16* __restrict__ Wd) {
+  const int l = blockIdx.y;
+  const int Ci = t.Ci[l], CK = t.CK[l], Co = t.Co[l];
+  const __nv_bfloat16* w = shadow + t.w_off[l];
+  const int nf = 9 * Co * CK;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf; i += gridDim.x * blockDim.x) {
+    const int ck = i % CK, co = (i / CK) % Co, tap = i / (CK * Co);
+    Wf[t.wf_off[l] + i] = ck < Ci ? w[(co * Ci + ck) * 9 + tap] : __float2bfloat16(0.f);
+  }
+  if (l > 0) {
+    const int nd = 9 * Ci * Co;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nd; i += gridDim.x * blockDim.x) {
+      const int co = i % Co, ci = (i / Co) % Ci, tap = i / (Co * Ci);
+      Wd[t.wd_off[l] + i] = w[(co * Ci + ci) * 9 + tap];
+    }
+  }
+}
+
+void conv_weight_relayout(const void* shadow, const ConvLayerTable& t, void* Wf, void* Wd, cudaStream_t st) {
+  dim3 grid(32, t.n);
+  conv_weight_relayout_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(shadow), t,
+                                                    reinterpret_cast<__nv_bfloat16*>(Wf),
+                                                    reinterpret_cast<__nv_bfloat16*>(Wd));
+  hefl::cuda::note_launch();
+}
+
+// dW32 [9*CK+1][Co] (wgrad output, row 9*CK = bias gradient) -> flat fp32 gradient in the
+// parameter layout ([Co][Ci][3][3], then bias); clears dW32 for the next step.
+__global__ void conv_grad_finalize_kernel(float* __restrict__ dW32, const ConvLayerTable t,
+                                          float* __restrict__ grad) {
+  const int l = blockIdx.y;
+  const int Ci = t.Ci[l], CK = t.CK[l], Co = t.Co[l];
+  float* src = dW32 + t.dw_off[l];
+  const int nw = Co * Ci * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += gridDim.x * blockDim.x) {
+    const int tap = i % 9, ci = (i / 9) % Ci, co = i / (9 * Ci);
+    grad[t.w_off[l] + i] = src[(size_t)(tap * CK + ci) * Co + co];
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Co; i += gridDim.x * blockDim.x)
+    grad[t.b_off[l] + i] = src[(size_t)9 * CK * Co + i];
+}
+__global__ void zero_f32_kernel(float* __restrict__ p, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0.f;
+}
+
+void conv_grad_finalize(float* dW32, const ConvLayerTable& t, float* grad, cudaStream_t st) {
+  dim3 grid(32, t.n);
+  conv_grad_finalize_kernel<<<grid, 256, 0, st>>>(dW32, t, grad);
+  const int l = t.n - 1;
+  const int64_t total = t.dw_off[l] + (int64_t)(9 * t.CK[l] + 1) * t.Co[l];
+  zero_f32_kernel<<<64, 256, 0, st>>>(dW32, total);
+  hefl::cuda::note_launch(2);
+}
+
+}  // namespace nn
+}  // namespace hefl

@@ -97,7 +97,8 @@ def build(verbose: bool = True, force: bool = False) -> Path:
         h = hashlib.sha256()
         h.update(src.read_bytes())
         h.update(hdr.encode())
-        h.update(" ".join(flags).encode())
+        # include paths differ between the CPU box and the GPU box; they do not change the object
+        h.update(" ".join(f for f in flags if not f.startswith("-I")).encode())
         return h.hexdigest()
 
     for rel in CUDA_SOURCES:

@@ -1,0 +1,168 @@
+"""Training engine for the sequential 3x3-conv CNNs on the hand-written tcgen05 kernels.
+
+Replaces Keras' ``model.fit`` compute path (FLPyfhelin.py:118-136, :193) for the medical CNN:
+
+  forward   preprocess_u8 (uint8 -> bf16 NHWC, 1/255, affine augmentation)
+            6 x conv_fwd_pool  (TMA-fed tcgen05 implicit GEMM, bias+ReLU+2x2 max-pool+argmax
+                                fused in the TMEM epilogue; only pooled tensors reach HBM)
+            dense head + softmax cross-entropy (tiny: PyTorch/cuBLAS autograd, fp32)
+  backward  6 x unpool_relu (pooled grad -> conv-grid grad in [P,C] and [C,P] layouts)
+            6 x conv_wgrad  (tcgen05, taps stacked along M, split-K, bias grad as a ones row)
+            5 x conv_dgrad  (tcgen05 tap GEMM with negative offsets)
+            conv_grad_finalize -> flat fp32 gradient, then the fused Adam kernel (trainer)
+
+All buffers are allocated once; the whole step is CUDA-graph capturable.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from .. import _ext
+from ..config import FLConfig
+from ..models.pack import ParamPack
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class MedCNNEngine:
+    def __init__(self, model, pack: ParamPack, cfg: FLConfig, device: torch.device):
+        if device.type != "cuda":
+            raise RuntimeError("the tcgen05 engine needs a CUDA device (sm_100a)")
+        self.ops = _ext.ops()
+        self.model, self.pack, self.cfg, self.device = model, pack, cfg, device
+        B, S = cfg.batch_size, cfg.image_size
+        if cfg.in_channels != 3:
+            raise ValueError("engine expects 3-channel uint8 images")
+        self.B = B
+        convs = list(model.convs)
+        self.n = len(convs)
+        offs = {k: o for k, _, o, _ in pack.entries}
+        keys = [k for k in pack.keras_order_keys()]
+        conv_keys = [(f"c_{2 * i}_0", f"c_{2 * i}_1") for i in range(self.n)]
+        self.H: List[int] = []
+        self.Ci: List[int] = []
+        self.CK: List[int] = []
+        self.Co: List[int] = []
+        h = S
+        for i, c in enumerate(convs):
+            ci, co = c.in_channels, c.out_channels
+            ck = 16 if i == 0 else ci
+            if ck not in (16, 32, 64) or co not in (32, 64, 128):
+                raise ValueError(f"unsupported conv shape ({ci}->{co}) for the tcgen05 engine")
+            self.H.append(h)
+            self.Ci.append(ci)
+            self.CK.append(ck)
+            self.Co.append(co)
+            h = (h - 2) // 2
+        self.H.append(h)                 # feature map side
+        bf = dict(dtype=torch.bfloat16, device=device)
+        self.P = [B * self.H[l] * self.H[l] for l in range(self.n + 1)]
+        # activations / gradients (all NHWC bf16 viewed as [pixels, channels])
+        self.X = [torch.zeros(self.P[0], 16, **bf)]
+        self.amax, self.dY, self.gX = [], [], [None]
+        for l in range(self.n):
+            hp = self.H[l + 1]
+            self.X.append(torch.zeros(B * hp * hp, self.Co[l], **bf))
+            self.amax.append(torch.zeros(B * hp * hp, self.Co[l], dtype=torch.uint8, device=device))
+            self.dY.append(torch.zeros(self.P[l], self.Co[l], **bf))
+            self.gX.append(torch.zeros(B * hp * hp, self.Co[l], **bf))
+        # weights
+        wf_off, wd_off, dw_off = [0], [0], [0]
+        for l in range(self.n):
+            wf_off.append(wf_off[-1] + 9 * self.Co[l] * self.CK[l])
+            wd_off.append(wd_off[-1] + 9 * self.Ci[l] * self.Co[l])
+            dw_off.append(dw_off[-1] + (9 * self.CK[l] + 1) * self.Co[l])
+        self.wf_off, self.wd_off, self.dw_off = wf_off, wd_off, dw_off
+        self.Wf = torch.zeros(wf_off[-1], **bf)
+        self.Wd = torch.zeros(wd_off[-1], **bf)
+        self.dW32 = torch.zeros(dw_off[-1], dtype=torch.float32, device=device)
+        self.shadow = torch.zeros(pack.n_trainable, **bf)
+        rows = []
+        self.b_off = []
+        for l, (kw, kb) in enumerate(conv_keys):
+            rows.append([self.Ci[l], self.CK[l], self.Co[l], offs[kw], offs[kb], wf_off[l], wd_off[l], dw_off[l]])
+            self.b_off.append(offs[kb])
+        self.table = torch.tensor(rows, dtype=torch.int64)
+        self.bias = [pack.flat[self.b_off[l]: self.b_off[l] + self.Co[l]] for l in range(self.n)]
+        self.theta = torch.zeros(B, 2, 3, dtype=torch.float32, device=device)
+        self.after_restore()
+
+    # ------------------------------------------------------------------ weights
+    def after_update(self) -> None:
+        """Called after Adam wrote the bf16 shadow: rebuild the tensor-core weight layouts."""
+        self.ops.conv_weight_relayout(self.shadow, self.table, self.Wf, self.Wd)
+
+    def after_restore(self) -> None:
+        self.shadow.copy_(self.pack.trainable())
+        self.after_update()
+
+    def _wf(self, l):
+        return self.Wf[self.wf_off[l]: self.wf_off[l + 1]]
+
+    def _wd(self, l):
+        return self.Wd[self.wd_off[l]: self.wd_off[l + 1]]
+
+    def _dw(self, l):
+        return self.dW32[self.dw_off[l]: self.dw_off[l + 1]]
+
+    # ------------------------------------------------------------------ forward
+    def _make_theta(self, shear=0.2, zoom=0.2) -> torch.Tensor:
+        B, dev = self.B, self.device
+        r = torch.rand(B, 4, device=dev)
+        sh = (r[:, 0] * 2 - 1) * shear * (math.pi / 180.0)
+        zx = 1.0 + (r[:, 1] * 2 - 1) * zoom
+        zy = 1.0 + (r[:, 2] * 2 - 1) * zoom
+        flip = torch.where(r[:, 3] < 0.5, -1.0, 1.0)
+        th = self.theta
+        th.zero_()
+        th[:, 0, 0] = zx * flip
+        th[:, 0, 1] = -torch.sin(sh) * zx
+        th[:, 1, 1] = torch.cos(sh) * zy
+        return th
+
+    def features(self, x_u8: torch.Tensor, train: bool, augment: bool) -> torch.Tensor:
+        theta = self._make_theta() if (train and augment) else None
+        self.ops.preprocess_u8(x_u8, theta, self.X[0])
+        for l in range(self.n):
+            h = self.H[l]
+            self.ops.conv_fwd_pool(self.X[l], self._wf(l), self.bias[l], self.X[l + 1],
+                                   self.amax[l] if train else None, self.B, h, h, self.CK[l], self.Co[l])
+        return self.X[self.n]
+
+    def _head(self, feat: torch.Tensor) -> torch.Tensor:
+        x = feat
+        fcs = self.model.fcs
+        for fc in fcs[:-1]:
+            x = F.relu(fc(x))
+        return fcs[-1](x)
+
+    # ------------------------------------------------------------------ steps
+    def train_step(self, x_u8: torch.Tensor, y: torch.Tensor, out: torch.Tensor, augment: bool = True) -> None:
+        feat_bf = self.features(x_u8, True, augment)
+        feat = feat_bf.view(self.B, -1).float().requires_grad_(True)
+        logits = self._head(feat)
+        loss = F.cross_entropy(logits, y)
+        loss.backward()
+        out[0] = loss.detach()
+        out[1] = (logits.argmax(1) == y).sum()
+        g = feat.grad.to(torch.bfloat16).view_as(feat_bf).contiguous()
+        for l in range(self.n - 1, -1, -1):
+            h = self.H[l]
+            self.ops.unpool_relu(g, self.amax[l], self.X[l + 1], self.dY[l], self.B, h, h, self.Co[l])
+            self.ops.conv_wgrad(self.X[l], self.dY[l], self._dw(l), self.P[l], h, self.CK[l], self.Co[l])
+            if l > 0:
+                self.ops.conv_dgrad(self.dY[l], self._wd(l), self.gX[l], self.B, h, h, self.Co[l], self.Ci[l])
+                g = self.gX[l]
+        self.ops.conv_grad_finalize(self.dW32, self.table, self.pack.grad)
+
+    def eval_step(self, x_u8: torch.Tensor, y: torch.Tensor, out: torch.Tensor) -> None:
+        feat = self.features(x_u8, False, False).view(self.B, -1).float()
+        logits = self._head(feat)
+        out[0] = F.cross_entropy(logits, y)
+        out[1] = (logits.argmax(1) == y).sum()

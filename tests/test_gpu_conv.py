@@ -1,0 +1,169 @@
+"""GPU tests of the tcgen05 convolution kernels against plain PyTorch fp32 references."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from hefl_b200 import _ext
+
+pytestmark = pytest.mark.gpu
+ops = _ext.ops()
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+def _rand_layer(B, H, Ci, CK, Co, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.zeros(B, H, H, CK, device="cuda")
+    x[..., :Ci] = torch.randn(B, H, H, Ci, device="cuda", generator=g)
+    w = torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) * (1.0 / (3 * Ci ** 0.5))
+    b = torch.randn(Co, device="cuda", generator=g) * 0.1
+    return _bf(x), _bf(w), b
+
+
+def _wf(w, CK):
+    Co, Ci = w.shape[:2]
+    out = torch.zeros(9, Co, CK, dtype=torch.bfloat16, device="cuda")
+    out[:, :, :Ci] = w.permute(2, 3, 0, 1).reshape(9, Co, Ci)
+    return out.contiguous()
+
+
+@pytest.mark.parametrize("B,H,Ci,CK,Co", [(2, 20, 3, 16, 32), (2, 30, 32, 32, 32), (3, 14, 32, 32, 64),
+                                          (2, 12, 64, 64, 64), (4, 6, 64, 64, 128), (2, 70, 32, 32, 32),
+                                          (1, 256, 3, 16, 32)])
+def test_conv_fwd_pool_matches_torch(B, H, Ci, CK, Co):
+    x, w, b = _rand_layer(B, H, Ci, CK, Co, 1)
+    Hp = (H - 2) // 2
+    out = torch.zeros(B * Hp * Hp, Co, dtype=torch.bfloat16, device="cuda")
+    am = torch.full((B * Hp * Hp, Co), 255, dtype=torch.uint8, device="cuda")
+    ops.conv_fwd_pool(x.view(-1, CK), _wf(w, CK), b, out, am, B, H, H, CK, Co)
+    torch.cuda.synchronize()
+    xr = x[..., :Ci].float().permute(0, 3, 1, 2)
+    y = F.relu(F.conv2d(xr, w.float(), b))
+    ref, idx = F.max_pool2d(y, 2, return_indices=True)
+    got = out.view(B, Hp, Hp, Co).permute(0, 3, 1, 2).float()
+    assert (got - ref).abs().max() <= 0.02 * ref.abs().max() + 1e-2
+    # argmax where the pooled value is positive: position inside the 2x2 window
+    Wo = H - 2
+    ih, iw = idx // Wo, idx % Wo
+    pos_ref = (ih % 2) * 2 + (iw % 2)
+    pos_got = am.view(B, Hp, Hp, Co).permute(0, 3, 1, 2).long()
+    sel = ref > 0.05
+    agree = (pos_ref[sel] == pos_got[sel]).float().mean()
+    assert agree > 0.995
+
+
+@pytest.mark.parametrize("B,H,Ci,Co", [(2, 30, 32, 32), (2, 14, 32, 64), (2, 12, 64, 64), (4, 6, 64, 128)])
+def test_conv_dgrad_matches_torch(B, H, Ci, Co):
+    g = torch.Generator(device="cuda").manual_seed(2)
+    Ho = H - 2
+    dyv = _bf(torch.randn(B, Co, Ho, Ho, device="cuda", generator=g))
+    w = _bf(torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) * 0.05)
+    dY = torch.zeros(B, H, H, Co, dtype=torch.bfloat16, device="cuda")
+    dY[:, :Ho, :Ho, :] = dyv.permute(0, 2, 3, 1)
+    Wd = w.permute(2, 3, 1, 0).reshape(9, Ci, Co).contiguous()      # [tap][ci][co]
+    dX = torch.zeros(B * H * H, Ci, dtype=torch.bfloat16, device="cuda")
+    ops.conv_dgrad(dY.view(-1, Co), Wd, dX, B, H, H, Co, Ci)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(dyv.float(), w.float())
+    got = dX.view(B, H, H, Ci).permute(0, 3, 1, 2).float()
+    assert (got - ref).abs().max() <= 0.02 * ref.abs().max() + 1e-2
+
+
+@pytest.mark.parametrize("B,H,Ci,CK,Co", [(2, 20, 3, 16, 32), (2, 30, 32, 32, 32), (2, 14, 32, 32, 64),
+                                          (2, 12, 64, 64, 64), (8, 6, 64, 64, 128), (4, 62, 32, 32, 32)])
+def test_conv_wgrad_matches_torch(B, H, Ci, CK, Co):
+    x, w, _ = _rand_layer(B, H, Ci, CK, Co, 3)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    Ho = H - 2
+    dyv = _bf(torch.randn(B, Co, Ho, Ho, device="cuda", generator=g))
+    dY = torch.zeros(B, H, H, Co, dtype=torch.bfloat16, device="cuda")
+    dY[:, :Ho, :Ho, :] = dyv.permute(0, 2, 3, 1)
+    P = B * H * H
+    dW32 = torch.zeros((9 * CK + 1) * Co, dtype=torch.float32, device="cuda")
+    ops.conv_wgrad(x.view(-1, CK), dY.view(-1, Co), dW32, P, H, CK, Co)
+    torch.cuda.synchronize()
+    xr = x[..., :Ci].float().permute(0, 3, 1, 2).requires_grad_(False)
+    wref = torch.nn.grad.conv2d_weight(xr, (Co, Ci, 3, 3), dyv.float())
+    got = dW32[: 9 * CK * Co].view(9, CK, Co)[:, :Ci, :].permute(2, 1, 0).reshape(Co, Ci, 3, 3)
+    assert (got - wref).abs().max() <= 0.02 * wref.abs().max() + 1e-2
+    bref = dyv.float().sum((0, 2, 3))
+    bgot = dW32[9 * CK * Co:]
+    assert (bgot - bref).abs().max() <= 0.02 * bref.abs().max() + 1e-2
+
+
+def test_unpool_relu_matches_autograd():
+    B, H, Co = 2, 14, 32
+    g = torch.Generator(device="cuda").manual_seed(5)
+    y = _bf(torch.randn(B, Co, H - 2, H - 2, device="cuda", generator=g)).float().requires_grad_(True)
+    pooled, idx = F.max_pool2d(F.relu(y), 2, return_indices=True)
+    gp = _bf(torch.randn_like(pooled))
+    pooled.backward(gp.float())
+    Hp = (H - 2) // 2
+    Wo = H - 2
+    pos = ((idx // Wo) % 2) * 2 + (idx % Wo) % 2
+    amax = pos.permute(0, 2, 3, 1).contiguous().to(torch.uint8).view(-1, Co)
+    P = B * H * H
+    dY = torch.zeros(P, Co, dtype=torch.bfloat16, device="cuda")
+    ops.unpool_relu(gp.permute(0, 2, 3, 1).contiguous().view(-1, Co), amax,
+                    _bf(pooled.detach()).permute(0, 2, 3, 1).contiguous().view(-1, Co), dY, B, H, H, Co)
+    torch.cuda.synchronize()
+    ref = torch.zeros(B, H, H, Co, device="cuda")
+    ref[:, : H - 2, : H - 2, :] = y.grad.permute(0, 2, 3, 1)
+    assert torch.equal(dY.view(B, H, H, Co).float(), ref)
+
+
+def test_preprocess_matches_grid_sample():
+    B, H = 4, 64
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = torch.randint(0, 256, (B, H, H, 3), dtype=torch.uint8, device="cuda", generator=g)
+    P = B * H * H
+    X = torch.zeros(P, 16, dtype=torch.bfloat16, device="cuda")
+    ops.preprocess_u8(x, None, X)
+    ref = x.float() / 255.0
+    assert (X.view(B, H, H, 16)[..., :3].float() - ref).abs().max() < 4e-3
+    assert float(X[:, 3:].abs().sum()) == 0.0
+    theta = torch.tensor([[[0.9, 0.05, 0.0], [0.0, 1.1, 0.0]]], device="cuda").repeat(B, 1, 1)
+    theta[1, 0, 0] *= -1
+    ops.preprocess_u8(x, theta.contiguous(), X)
+    xr = (x.float() / 255.0).permute(0, 3, 1, 2)
+    grid = F.affine_grid(theta, list(xr.shape), align_corners=False)
+    ref = F.grid_sample(xr, grid, mode="bilinear", padding_mode="border", align_corners=False).permute(0, 2, 3, 1)
+    assert (X.view(B, H, H, 16)[..., :3].float() - ref).abs().max() < 1e-2
+
+
+def test_engine_gradients_match_autograd():
+    """Whole medical CNN: engine forward/backward vs PyTorch autograd on the same weights."""
+    from hefl_b200.config import FLConfig
+    from hefl_b200.models import ParamPack, create_model
+    from hefl_b200.ops.conv_engine import MedCNNEngine
+
+    torch.manual_seed(0)
+    cfg = FLConfig(model="medcnn", batch_size=8, image_size=256)
+    dev = torch.device("cuda")
+    model = create_model("medcnn").to(dev)
+    pack = ParamPack(model)
+    # round the weights to bf16 so both paths see identical parameters
+    pack.flat.copy_(pack.flat.to(torch.bfloat16).float())
+    eng = MedCNNEngine(model, pack, cfg, dev)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randint(0, 256, (8, 256, 256, 3), dtype=torch.uint8, device="cuda", generator=g)
+    y = torch.randint(0, 2, (8,), device="cuda", generator=g)
+    out = torch.zeros(2, device="cuda")
+    eng.train_step(x, y, out, augment=False)
+    torch.cuda.synchronize()
+    g_eng = pack.grad.clone()
+    pack.grad.zero_()
+    xr = (x.float() / 255.0).to(torch.bfloat16).float().permute(0, 3, 1, 2)
+    logits = model(xr)
+    loss = F.cross_entropy(logits, y)
+    loss.backward()
+    g_ref = pack.grad.clone()
+    assert abs(float(out[0]) - float(loss)) < 2e-2
+    for key, shape, off, n in pack.entries:
+        a, b = g_eng[off:off + n], g_ref[off:off + n]
+        denom = b.abs().max().item() + 1e-6
+        rel = (a - b).abs().max().item() / denom
+        cos = F.cosine_similarity(a, b, dim=0).item() if b.norm() > 0 else 1.0
+        assert cos > 0.98 and rel < 0.2, (key, rel, cos)

@@ -6,9 +6,10 @@
 // with h >= H-2 or w >= W-2 are garbage and masked). Each tap's A tile is therefore one plain
 // 2-D TMA box — no im2col buffer, no gather.
 //
-//   conv_fwd_pool : per CTA tile = 2 image rows x 64 columns (128 GEMM rows) so that the
-//                   epilogue can do bias + ReLU + 2x2 max-pool + argmax straight out of TMEM and
-//                   write only the pooled tensor (4x less HBM traffic than the conv output).
+//   conv_fwd_pool : per CTA tile = 2 image rows x 128 columns (two TMEM accumulators) so that the
+//                   epilogue does bias + ReLU + 2x2 max-pool + argmax straight out of TMEM (vertical
+//                   max in-thread across the two accumulators, horizontal max by one shuffle) and
+//                   writes only the pooled tensor (4x less HBM traffic than the conv output).
 //   conv_dgrad    : dX[m,:] = sum_taps dY[m - off, :] * W[r,s]   (same kernel, negative offsets,
 //                   plain bf16 store).
 //   conv_wgrad    : dW[r,s] = sum_m X[m+off,:]^T dY[m,:]. Both operands are consumed in their
@@ -18,9 +19,9 @@
 //                   bias gradient (an all-ones tap atom).
 //
 // Warp roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
-// warps 2..5 = epilogue (TMEM -> registers -> global). smem ring of NSTAGE tap tiles with
-// full/empty mbarriers; two TMEM accumulators so the epilogue of tile i overlaps the MMAs of
-// tile i+1. Weights for all 9 taps stay resident in shared memory for the CTA's lifetime.
+// warps 2..5 = epilogue (TMEM -> registers -> global). smem ring of halo tiles with full/empty
+// mbarriers; two TMEM tile buffers so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Weights for all 9 taps stay resident in shared memory for the CTA's lifetime.
 #include <cuda_bf16.h>
 
 #include <cstdio>
@@ -90,7 +91,17 @@ static int num_sms() {
 }
 
 // ------------------------------------------------------------------------------------------
-// G1: tap-GEMM kernel (forward + pool epilogue, or dgrad with plain store)
+// G1: halo-tile tap-GEMM kernel (forward + pool epilogue, or dgrad with plain store)
+//
+// Measured on B200 (bench/probe_shift.py): a K-major swizzled tile written by TMA can be read by
+// tcgen05.mma starting at ANY row (descriptor start address + rows*row_bytes, base_offset 0) —
+// the swizzle is a function of absolute shared-memory address bits. So each input row segment
+// is loaded ONCE per tile and all 9 taps address shifted windows of it:
+//   forward : tile = 2 image rows x 128 columns; 4 halo segments (rows h..h+3) of 130 pixels;
+//             accumulator j (row h+j), tap (r,s) reads segment j+r at row offset s.
+//   dgrad   : tile = 128 consecutive pixels; 3 segments starting at m0 - r*W - 2; tap (r,s)
+//             reads segment r at row offset 2 - s.
+// L2->SM traffic drops from 9 tap tiles to ~2 (fwd) / ~3 (dgrad) tiles per output tile.
 // ------------------------------------------------------------------------------------------
 struct TapGemmArgs {
   int B, H, W;          // input grid of the A matrix
@@ -98,7 +109,7 @@ struct TapGemmArgs {
   int tiles_w;          // column tiles per row pair (POOL)
   int num_tiles;
   int P;                // B*H*W
-  int sign;             // +1 forward (m + off), -1 dgrad (m - off)
+  int co_total;         // output channels of the layer (CO per CTA column block = blockIdx.y)
   const float* bias;    // [CO] (POOL)
   __nv_bfloat16* out;   // POOL: [B,Hp,Wp,CO]; else [P,CO]
   uint8_t* argmax;      // POOL, may be null
@@ -109,19 +120,23 @@ struct TapGemmCfg {
   static constexpr int KB = CK < 64 ? CK : 64;            // channels per k-block (one swizzle atom)
   static constexpr int NKB = CK / KB;
   static constexpr int ROW_BYTES = KB * 2;
-  static constexpr int A_SUB = 128 * ROW_BYTES;           // one k-block of one tap tile
-  static constexpr int A_STAGE = A_SUB * NKB;
+  static constexpr int NSEG = POOL ? 4 : 3;
+  static constexpr int NACC = POOL ? 2 : 1;
+  static constexpr int SEG_ROWS = 136;                    // 130 used, multiple of 8
+  static constexpr int SEG_BYTES = SEG_ROWS * ROW_BYTES;
+  static constexpr int HALO = NKB * NSEG * SEG_BYTES;     // one tile's input
   static constexpr int W_SUB = CO * ROW_BYTES;
   static constexpr int W_TAP = W_SUB * NKB;
   static constexpr int W_BYTES = 9 * W_TAP;
-  static constexpr int EXCH = POOL ? (2 * 32 * 16 * 4 + 2 * 32 * 16) : 0;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int BUDGET = 224 * 1024;
-  static constexpr int NSTAGE_RAW = (BUDGET - W_BYTES - EXCH - BAR_BYTES - 1024) / A_STAGE;
-  static constexpr int NSTAGE = NSTAGE_RAW > 6 ? 6 : NSTAGE_RAW;
-  static constexpr int SMEM = W_BYTES + NSTAGE * A_STAGE + EXCH + BAR_BYTES + 1024;
-  static constexpr int TMEM_COLS = 2 * CO <= 32 ? 32 : (2 * CO <= 64 ? 64 : (2 * CO <= 128 ? 128 : 256));
-  static_assert(NSTAGE >= 2, "not enough shared memory for a 2-stage pipeline");
+  static constexpr int BUDGET = 225 * 1024;
+  static constexpr int NBUF_RAW = (BUDGET - W_BYTES - BAR_BYTES - 1024) / HALO;
+  static constexpr int NBUF = NBUF_RAW > 3 ? 3 : NBUF_RAW;
+  static constexpr int SMEM = W_BYTES + NBUF * HALO + BAR_BYTES + 1024;
+  static constexpr int ACC_COLS = 2 * NACC * CO;          // two tile buffers
+  static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
+  static_assert(NBUF >= 1, "halo tile does not fit in shared memory");
+  static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
   static_assert(CO % 32 == 0 && CO <= 128, "CO must be 32, 64, 96 or 128");
 };
 
@@ -134,12 +149,10 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;
   uint8_t* sA = smem + Cfg::W_BYTES;
-  float* exch_v = reinterpret_cast<float*>(sA + Cfg::NSTAGE * Cfg::A_STAGE);
-  uint8_t* exch_i = reinterpret_cast<uint8_t*>(exch_v) + 2 * 32 * 16 * 4;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + Cfg::NSTAGE * Cfg::A_STAGE + Cfg::EXCH);
-  uint64_t* full = bars;                       // [NSTAGE]
-  uint64_t* empty = bars + Cfg::NSTAGE;        // [NSTAGE]
-  uint64_t* wfull = bars + 2 * Cfg::NSTAGE;    // [1]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + Cfg::NBUF * Cfg::HALO);
+  uint64_t* full = bars;                       // [NBUF]
+  uint64_t* empty = bars + Cfg::NBUF;          // [NBUF]
+  uint64_t* wfull = bars + 2 * Cfg::NBUF;      // [1]
   uint64_t* tfull = wfull + 1;                 // [2]
   uint64_t* tempty = tfull + 2;                // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
@@ -150,7 +163,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmW);
-    for (int s = 0; s < Cfg::NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < Cfg::NBUF; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(wfull, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
     fence_barrier_init();
@@ -167,37 +180,32 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_expect_tx(wfull, Cfg::W_BYTES);
       for (int tap = 0; tap < 9; ++tap)
         for (int kb = 0; kb < Cfg::NKB; ++kb)
-          tma_load_2d(sW + tap * Cfg::W_TAP + kb * Cfg::W_SUB, &tmW, kb * Cfg::KB, tap * CO, wfull);
-      int stage = 0;
+          tma_load_2d(sW + tap * Cfg::W_TAP + kb * Cfg::W_SUB, &tmW, kb * Cfg::KB,
+                      tap * a.co_total + blockIdx.y * CO, wfull);
+      int buf = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-        int base0, base1 = 0;
+        int base, seg_stride;
         if (POOL) {
           const int per_img = a.Hp * a.tiles_w;
           const int b = t / per_img;
           const int rem = t - b * per_img;
           const int hp = rem / a.tiles_w;
           const int tw = rem - hp * a.tiles_w;
-          base0 = (b * a.H + 2 * hp) * a.W + tw * 64;
-          base1 = base0 + a.W;
+          base = (b * a.H + 2 * hp) * a.W + tw * 128;
+          seg_stride = a.W;                      // segment j = image row h + j
         } else {
-          base0 = t * 128;
+          base = t * 128 - 2;
+          seg_stride = -a.W;                     // segment r starts at m0 - r*W - 2
         }
-        for (int tap = 0; tap < 9; ++tap) {
-          const int off = a.sign * ((tap / 3) * a.W + (tap % 3));
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], Cfg::A_STAGE);
-          uint8_t* dst = sA + stage * Cfg::A_STAGE;
-          for (int kb = 0; kb < Cfg::NKB; ++kb) {
-            if (POOL) {
-              tma_load_2d(dst + kb * Cfg::A_SUB, &tmA, kb * Cfg::KB, base0 + off, &full[stage]);
-              tma_load_2d(dst + kb * Cfg::A_SUB + 64 * Cfg::ROW_BYTES, &tmA, kb * Cfg::KB, base1 + off, &full[stage]);
-            } else {
-              tma_load_2d(dst + kb * Cfg::A_SUB, &tmA, kb * Cfg::KB, base0 + off, &full[stage]);
-            }
-          }
-          if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
-        }
+        mbar_wait(&empty[buf], phase ^ 1);
+        mbar_expect_tx(&full[buf], Cfg::HALO);
+        uint8_t* dst = sA + buf * Cfg::HALO;
+        for (int kb = 0; kb < Cfg::NKB; ++kb)
+          for (int sg = 0; sg < Cfg::NSEG; ++sg)
+            tma_load_2d(dst + (kb * Cfg::NSEG + sg) * Cfg::SEG_BYTES, &tmA, kb * Cfg::KB, base + sg * seg_stride,
+                        &full[buf]);
+        if (++buf == Cfg::NBUF) { buf = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -205,45 +213,53 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr uint32_t idesc = make_idesc_bf16(128, CO);
     mbar_wait(wfull, 0);
     tc_fence_after();
-    int stage = 0;
+    int buf = 0;
     uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    int tb = 0;
+    uint32_t tb_phase = 0;
     for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      mbar_wait(&tempty[tb], tb_phase ^ 1);
+      mbar_wait(&full[buf], phase);
       tc_fence_after();
-      for (int tap = 0; tap < 9; ++tap) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_STAGE);
-          const uint32_t w_addr = smem_u32(sW + tap * Cfg::W_TAP);
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(sA + buf * Cfg::HALO);
+        const uint32_t w_addr = smem_u32(sW);
 #pragma unroll
-          for (int kb = 0; kb < Cfg::NKB; ++kb) {
+        for (int j = 0; j < Cfg::NACC; ++j) {
+          const uint32_t d_tmem = tmem_base + (tb * Cfg::NACC + j) * CO;
 #pragma unroll
-            for (int k = 0; k < Cfg::KB / 16; ++k) {
-              const uint64_t ad = make_kmajor_desc(a_addr + kb * Cfg::A_SUB + k * 32, Cfg::ROW_BYTES);
-              const uint64_t bd = make_kmajor_desc(w_addr + kb * Cfg::W_SUB + k * 32, Cfg::ROW_BYTES);
-              umma_bf16(tmem_base + acc * CO, ad, bd, idesc, (tap | kb | k) != 0 ? 1u : 0u);
+          for (int tap = 0; tap < 9; ++tap) {
+            const int r = tap / 3, s = tap % 3;
+            const int seg = POOL ? (j + r) : r;
+            const int shift = POOL ? s : (2 - s);
+#pragma unroll
+            for (int kb = 0; kb < Cfg::NKB; ++kb) {
+#pragma unroll
+              for (int k = 0; k < Cfg::KB / 16; ++k) {
+                const uint64_t ad = make_kmajor_desc(
+                    a_addr + (kb * Cfg::NSEG + seg) * Cfg::SEG_BYTES + shift * Cfg::ROW_BYTES + k * 32, Cfg::ROW_BYTES);
+                const uint64_t bd = make_kmajor_desc(w_addr + tap * Cfg::W_TAP + kb * Cfg::W_SUB + k * 32, Cfg::ROW_BYTES);
+                umma_bf16(d_tmem, ad, bd, idesc, (tap | kb | k) != 0 ? 1u : 0u);
+              }
             }
           }
-          umma_commit(&empty[stage]);
-          if (tap == 8) umma_commit(&tfull[acc]);
         }
-        __syncwarp();
-        if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
+        umma_commit(&empty[buf]);
+        umma_commit(&tfull[tb]);
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      __syncwarp();
+      if (++buf == Cfg::NBUF) { buf = 0; phase ^= 1; }
+      tb ^= 1;
+      if (tb == 0) tb_phase ^= 1;
     }
   } else {
     // ===== epilogue warps (2..5) =====
     const int qd = warp & 3;                       // TMEM lane quadrant this warp may read
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    int tb = 0;
+    uint32_t tb_phase = 0;
     for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-      mbar_wait(&tfull[acc], acc_phase);
+      mbar_wait(&tfull[tb], tb_phase);
       tc_fence_after();
       if (POOL) {
         const int per_img = a.Hp * a.tiles_w;
@@ -251,49 +267,41 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int rem = t - b * per_img;
         const int hp = rem / a.tiles_w;
         const int tw = rem - hp * a.tiles_w;
-        const int col = tw * 64 + (qd & 1) * 32 + lane;      // conv-output column of this thread
+        const int col = tw * 128 + qd * 32 + lane;           // conv-output column of this thread
         const int wp = col >> 1;
-        const bool lower = qd >= 2;                          // image row h+1
-        const bool even = (lane & 1) == 0;
-        const int slot = lane >> 1;
-        const int half = qd & 1;
+        const bool writer = ((lane & 1) == 0) && wp < a.Wp;
 #pragma unroll 1
         for (int ch = 0; ch < CO / 32; ++ch) {
-          float v[32];
-          tmem_ld32(tmem_base + lane_base + acc * CO + ch * 32, v);
-          uint32_t hbits = 0;
+          float v0[32], v1[32];
+          tmem_ld32(tmem_base + lane_base + (tb * 2 + 0) * CO + ch * 32, v0);
+          tmem_ld32(tmem_base + lane_base + (tb * 2 + 1) * CO + ch * 32, v1);
+          uint32_t vbits = 0;                                 // 1 = lower image row wins
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
-            float x = v[c] + __ldg(a.bias + ch * 32 + c);
-            x = x > 0.f ? x : 0.f;
+            const float bsv = __ldg(a.bias + ch * 32 + c);
+            float x0 = v0[c] + bsv, x1 = v1[c] + bsv;
+            x0 = x0 > 0.f ? x0 : 0.f;
+            x1 = x1 > 0.f ? x1 : 0.f;
+            if (x1 > x0) { x0 = x1; vbits |= 1u << c; }
+            v0[c] = x0;
+          }
+          const uint32_t pvbits = __shfl_xor_sync(0xffffffffu, vbits, 1);
+          uint32_t packed[16];
+          uint32_t idx4[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) idx4[i] = 0;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float x = v0[c];
             const float o = __shfl_xor_sync(0xffffffffu, x, 1);
-            if (o > x) { x = o; hbits |= 1u << c; }        // meaningful on even lanes only
-            v[c] = x;
+            uint32_t id = ((vbits >> c) & 1u) * 2u;
+            if (o > x) { x = o; id = ((pvbits >> c) & 1u) * 2u + 1u; }
+            const uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(x));
+            if (c & 1) packed[c >> 1] |= hb << 16; else packed[c >> 1] = hb;
+            idx4[c >> 2] |= id << ((c & 3) * 8);
           }
-          if (lower && even) {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              exch_v[(half * 32 + c) * 16 + slot] = v[c];
-              exch_i[(half * 32 + c) * 16 + slot] = (uint8_t)((hbits >> c) & 1u);
-            }
-          }
-          named_barrier_sync(1, 128);
-          if (!lower && even && wp < a.Wp) {
+          if (writer) {
             const size_t o = ((size_t)(b * a.Hp + hp) * a.Wp + wp) * CO + ch * 32;
-            uint32_t packed[16];
-            uint32_t idx4[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) idx4[i] = 0;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              float x = v[c];
-              uint32_t id = (hbits >> c) & 1u;
-              const float pv = exch_v[(half * 32 + c) * 16 + slot];
-              if (pv > x) { x = pv; id = 2u + exch_i[(half * 32 + c) * 16 + slot]; }
-              const uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(x));
-              if (c & 1) packed[c >> 1] |= hb << 16; else packed[c >> 1] = hb;
-              idx4[c >> 2] |= id << ((c & 3) * 8);
-            }
             uint4* dst = reinterpret_cast<uint4*>(a.out + o);
 #pragma unroll
             for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
@@ -303,14 +311,13 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               di[1] = make_uint4(idx4[4], idx4[5], idx4[6], idx4[7]);
             }
           }
-          named_barrier_sync(1, 128);
         }
       } else {
         const int m = t * 128 + qd * 32 + lane;
 #pragma unroll 1
         for (int ch = 0; ch < CO / 32; ++ch) {
           float v[32];
-          tmem_ld32(tmem_base + lane_base + acc * CO + ch * 32, v);
+          tmem_ld32(tmem_base + lane_base + tb * CO + ch * 32, v);
           if (m < a.P) {
             uint32_t packed[16];
 #pragma unroll
@@ -319,7 +326,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               const uint32_t hi = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(v[c + 1]));
               packed[c >> 1] = lo | (hi << 16);
             }
-            uint4* dst = reinterpret_cast<uint4*>(a.out + (size_t)m * CO + ch * 32);
+            uint4* dst = reinterpret_cast<uint4*>(a.out + (size_t)m * a.co_total + blockIdx.y * CO + ch * 32);
 #pragma unroll
             for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
           }
@@ -327,9 +334,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (lane == 0) mbar_arrive(&tempty[tb]);
+      tb ^= 1;
+      if (tb == 0) tb_phase ^= 1;
     }
   }
   tc_fence_before();
@@ -343,12 +350,14 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 template <int CK, int CO, bool POOL>
 static void launch_tap_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Wt, TapGemmArgs a, cudaStream_t st) {
   using Cfg = TapGemmCfg<CK, CO, POOL>;
-  const CUtensorMap tmA = make_map(A, CK, (uint64_t)a.P, (uint64_t)CK * 2, Cfg::KB, POOL ? 64 : 128);
-  const CUtensorMap tmW = make_map(Wt, CK, (uint64_t)9 * CO, (uint64_t)CK * 2, Cfg::KB, CO);
+  const CUtensorMap tmA = make_map(A, CK, (uint64_t)a.P, (uint64_t)CK * 2, Cfg::KB, Cfg::SEG_ROWS);
+  const CUtensorMap tmW = make_map(Wt, CK, (uint64_t)9 * a.co_total, (uint64_t)CK * 2, Cfg::KB, CO);
   auto kern = tap_gemm_kernel<CK, CO, POOL>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-  int grid = a.num_tiles < num_sms() ? a.num_tiles : num_sms();
-  if (grid < 1) grid = 1;
+  const int ny = a.co_total / CO;
+  int gx = a.num_tiles < num_sms() / ny ? a.num_tiles : num_sms() / ny;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, ny);
   kern<<<grid, 192, Cfg::SMEM, st>>>(tmA, tmW, a);
   hefl::cuda::note_launch();
 }
@@ -358,10 +367,10 @@ void conv_fwd_pool(const void* X, const void* Wf, const float* bias, void* out, 
   TapGemmArgs a{};
   a.B = B; a.H = H; a.W = W;
   a.Hp = (H - 2) / 2; a.Wp = (W - 2) / 2;
-  a.tiles_w = (2 * a.Wp + 63) / 64;
+  a.tiles_w = (2 * a.Wp + 127) / 128;
   a.num_tiles = B * a.Hp * a.tiles_w;
   a.P = B * H * W;
-  a.sign = 1;
+  a.co_total = CO;
   a.bias = bias;
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
   a.argmax = argmax;
@@ -380,14 +389,14 @@ void conv_dgrad(const void* dY, const void* Wd, void* dX, int B, int H, int W, i
   a.B = B; a.H = H; a.W = W;
   a.P = B * H * W;
   a.num_tiles = (a.P + 127) / 128;
-  a.sign = -1;
+  a.co_total = CO;
   a.out = reinterpret_cast<__nv_bfloat16*>(dX);
   const auto* x = reinterpret_cast<const __nv_bfloat16*>(dY);
   const auto* w = reinterpret_cast<const __nv_bfloat16*>(Wd);
   if (CK == 32 && CO == 32) launch_tap_gemm<32, 32, false>(x, w, a, st);
   else if (CK == 64 && CO == 32) launch_tap_gemm<64, 32, false>(x, w, a, st);
   else if (CK == 64 && CO == 64) launch_tap_gemm<64, 64, false>(x, w, a, st);
-  else if (CK == 128 && CO == 64) launch_tap_gemm<128, 64, false>(x, w, a, st);
+  else if (CK == 128 && CO == 64) launch_tap_gemm<128, 32, false>(x, w, a, st);   // two column blocks
   else throw std::runtime_error("conv_dgrad: unsupported (CK, CO)");
 }
 
@@ -571,6 +580,77 @@ void conv_wgrad(const void* X, const void* DY, float* dW32, int P, int W, int CK
   else if (CK == 64 && Co == 64) launch_wgrad<64, 64>(x, d, a, Co, st);
   else if (CK == 64 && Co == 128) launch_wgrad<64, 64>(x, d, a, Co, st);
   else throw std::runtime_error("conv_wgrad: unsupported (CK, Co)");
+}
+
+}  // namespace nn
+}  // namespace hefl
+
+// ------------------------------------------------------------------------------------------
+// Probe: can a K-major swizzled A tile be consumed starting at an arbitrary ROW offset (with the
+// descriptor's base_offset field carrying the swizzle phase)? Used to validate halo-tile reuse.
+// ------------------------------------------------------------------------------------------
+namespace hefl {
+namespace nn {
+using namespace hefl::tc;
+
+template <int CK>
+__global__ void __launch_bounds__(128, 1)
+umma_shift_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        float* out, int shift_rows, int mode) {
+  constexpr int RB = CK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                      // 144 rows
+  uint8_t* sB = smem + 144 * 128;          // 32 rows
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 32 * 128);
+  uint64_t* done = bar + 1;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(done, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<32>(slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, 144 * RB + 32 * RB);
+    tma_load_2d(sA, &tmA, 0, 0, bar);
+    tma_load_2d(sB, &tmB, 0, 0, bar);
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    const uint32_t a0 = smem_u32(sA) + shift_rows * RB;
+    for (int k = 0; k < CK / 16; ++k) {
+      uint64_t ad = make_kmajor_desc(a0 + k * 32, RB);
+      if (mode == 1) ad |= (uint64_t)((a0 >> 7) & 7) << 49;   // base_offset = row phase in the 1024-B pattern
+      const uint64_t bd = make_kmajor_desc(smem_u32(sB) + k * 32, RB);
+      umma_bf16(tmem, ad, bd, make_idesc_bf16(128, 32), k ? 1u : 0u);
+    }
+    umma_commit(done);
+  }
+  mbar_wait(done, 0);
+  tc_fence_after();
+  float v[32];
+  tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
+  for (int c = 0; c < 32; ++c) out[(warp * 32 + lane) * 32 + c] = v[c];
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<32>(tmem); }
+}
+
+void umma_shift_probe(const void* A, const void* Bm, float* out, int CK, int shift_rows, int mode, cudaStream_t st) {
+  const CUtensorMap tmA = make_map(A, CK, 144, (uint64_t)CK * 2, CK, 144);
+  const CUtensorMap tmB = make_map(Bm, CK, 32, (uint64_t)CK * 2, CK, 32);
+  const int smem = 144 * 128 + 32 * 128 + 64 + 1024;
+  if (CK == 64) {
+    cudaFuncSetAttribute(umma_shift_probe_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    umma_shift_probe_kernel<64><<<1, 128, smem, st>>>(tmA, tmB, out, shift_rows, mode);
+  } else if (CK == 32) {
+    cudaFuncSetAttribute(umma_shift_probe_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    umma_shift_probe_kernel<32><<<1, 128, smem, st>>>(tmA, tmB, out, shift_rows, mode);
+  } else {
+    cudaFuncSetAttribute(umma_shift_probe_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    umma_shift_probe_kernel<16><<<1, 128, smem, st>>>(tmA, tmB, out, shift_rows, mode);
+  }
 }
 
 }  // namespace nn

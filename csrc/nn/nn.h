@@ -19,6 +19,8 @@ void conv_fwd_pool(const void* X, const void* Wf, const float* bias, void* out, 
 void conv_dgrad(const void* dY, const void* Wd, void* dX, int B, int H, int W, int CK, int CO, cudaStream_t st);
 void conv_wgrad(const void* X, const void* DY, float* dW32, int P, int W, int CK, int Co, cudaStream_t st);
 
+void umma_shift_probe(const void* A, const void* Bm, float* out, int CK, int shift_rows, int mode, cudaStream_t st);
+
 // ---- data-movement kernels around the convolutions (nn_kernels.cu) ----
 constexpr int kMaxConvLayers = 8;
 struct ConvLayerTable {
@@ -28,7 +30,8 @@ struct ConvLayerTable {
   int64_t wf_off[kMaxConvLayers], wd_off[kMaxConvLayers];     // offsets (elements) into the bf16 Wf / Wd buffers
   int64_t dw_off[kMaxConvLayers];                             // offsets (elements) into the fp32 dW32 buffer
 };
-void preprocess_u8(const uint8_t* x, const float* theta, void* X, int B, int H, int W, cudaStream_t st);
+void preprocess_u8(const uint8_t* x, const float* theta, void* X, int B, int H, int W, uint64_t aug_seed,
+                   const int64_t* step, cudaStream_t st);
 void unpool_relu(const void* g, const uint8_t* amax, const void* ypool, void* dY, int B, int H, int W, int Hp,
                  int Wp, int Co, cudaStream_t st);
 void conv_weight_relayout(const void* shadow, const ConvLayerTable& t, void* Wf, void* Wd, cudaStream_t st);

@@ -107,7 +107,8 @@ void conv_wgrad(const Tensor& X, const Tensor& DY, Tensor dW32, int64_t P, int64
   hefl::nn::conv_wgrad(X.data_ptr(), DY.data_ptr(), dW32.data_ptr<float>(), (int)P, (int)W, (int)CK, (int)Co, cur());
 }
 
-void preprocess_u8(const Tensor& x, const c10::optional<Tensor>& theta, Tensor X) {
+void preprocess_u8(const Tensor& x, const c10::optional<Tensor>& theta, Tensor X, int64_t aug_seed,
+                   const c10::optional<Tensor>& step) {
   TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kByte && x.is_contiguous() && x.dim() == 4 && x.size(3) == 3, "x must be uint8 [B,H,W,3]");
   chk_bf16(X, "X");
   const int64_t B = x.size(0), H = x.size(1), W = x.size(2);
@@ -117,7 +118,12 @@ void preprocess_u8(const Tensor& x, const c10::optional<Tensor>& theta, Tensor X
     TORCH_CHECK(theta->is_cuda() && theta->scalar_type() == at::kFloat && theta->numel() == B * 6 && theta->is_contiguous(), "theta must be float32 [B,2,3]");
     th = theta->data_ptr<float>();
   }
-  hefl::nn::preprocess_u8(x.data_ptr<uint8_t>(), th, X.data_ptr(), (int)B, (int)H, (int)W, cur());
+  const int64_t* sp = nullptr;
+  if (step.has_value()) {
+    TORCH_CHECK(step->is_cuda() && step->scalar_type() == at::kLong && step->numel() == 1, "step must be a CUDA int64 scalar tensor");
+    sp = step->data_ptr<int64_t>();
+  }
+  hefl::nn::preprocess_u8(x.data_ptr<uint8_t>(), th, X.data_ptr(), (int)B, (int)H, (int)W, (uint64_t)aug_seed, sp, cur());
 }
 
 void unpool_relu(const Tensor& g, const Tensor& amax, const Tensor& ypool, Tensor dY, int64_t B, int64_t H,
@@ -130,6 +136,14 @@ void unpool_relu(const Tensor& g, const Tensor& amax, const Tensor& ypool, Tenso
   TORCH_CHECK(Co % 8 == 0, "Co must be a multiple of 8");
   hefl::nn::unpool_relu(g.data_ptr(), amax.data_ptr<uint8_t>(), ypool.data_ptr(), dY.data_ptr(), (int)B, (int)H,
                         (int)W, (int)Hp, (int)Wp, (int)Co, cur());
+}
+
+Tensor umma_shift_probe(const Tensor& A, const Tensor& Bm, int64_t CK, int64_t shift_rows, int64_t mode) {
+  chk_bf16(A, "A"); chk_bf16(Bm, "Bm");
+  TORCH_CHECK(A.numel() == 144 * CK && Bm.numel() == 32 * CK, "A must be [144,CK], B [32,CK]");
+  Tensor out = at::zeros({128, 32}, A.options().dtype(at::kFloat));
+  hefl::nn::umma_shift_probe(A.data_ptr(), Bm.data_ptr(), out.data_ptr<float>(), (int)CK, (int)shift_rows, (int)mode, cur());
+  return out;
 }
 
 hefl::nn::ConvLayerTable table_from(const Tensor& t) {
@@ -164,8 +178,9 @@ TORCH_LIBRARY_FRAGMENT(hefl, m) {
   m.def("conv_fwd_pool(Tensor X, Tensor Wf, Tensor bias, Tensor(a!) out, Tensor(b!)? argmax, int B, int H, int W, int CK, int CO) -> ()", &conv_fwd_pool);
   m.def("conv_dgrad(Tensor dY, Tensor Wd, Tensor(a!) dX, int B, int H, int W, int CK, int CO) -> ()", &conv_dgrad);
   m.def("conv_wgrad(Tensor X, Tensor DY, Tensor(a!) dW32, int P, int W, int CK, int Co) -> ()", &conv_wgrad);
-  m.def("preprocess_u8(Tensor x, Tensor? theta, Tensor(a!) X) -> ()", &preprocess_u8);
+  m.def("preprocess_u8(Tensor x, Tensor? theta, Tensor(a!) X, int aug_seed, Tensor? step) -> ()", &preprocess_u8);
   m.def("unpool_relu(Tensor g, Tensor amax, Tensor ypool, Tensor(a!) dY, int B, int H, int W, int Co) -> ()", &unpool_relu);
+  m.def("umma_shift_probe(Tensor A, Tensor Bm, int CK, int shift_rows, int mode) -> Tensor", &umma_shift_probe);
   m.def("conv_weight_relayout(Tensor shadow, Tensor table, Tensor(a!) Wf, Tensor(b!) Wd) -> ()", &conv_weight_relayout);
   m.def("conv_grad_finalize(Tensor(a!) dW32, Tensor table, Tensor(b!) grad) -> ()", &conv_grad_finalize);
 }

@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 
 #include "../he/kernels.h"
+#include "../he/philox.h"
 #include "nn.h"
 
 namespace hefl {
@@ -55,15 +56,36 @@ namespace nn {
 // FLPyfhelin.py:80-86) sampled bilinearly with border clamp (torch.grid_sample semantics,
 // align_corners=False).
 __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ x, const float* __restrict__ theta,
-                                     __nv_bfloat16* __restrict__ X, int B, int H, int W) {
-  const int64_t P = (int64_t)B * H * W;
-  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < P; m += (int64_t)gridDim.x * blockDim.x) {
-    const int w = (int)(m % W);
-    const int h = (int)((m / W) % H);
-    const int b = (int)(m / ((int64_t)W * H));
+                                     __nv_bfloat16* __restrict__ X, int B, int H, int W, uint64_t aug_seed,
+                                     const int64_t* __restrict__ step) {
+  const int b = blockIdx.y;
+  const int HW = H * W;
+  float tl[6];
+  bool warp_img = theta != nullptr;
+  if (theta) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) tl[i] = theta[b * 6 + i];
+  } else if (aug_seed != 0) {
+    // Keras ImageDataGenerator(shear_range=0.2 deg, zoom_range=0.2, horizontal_flip) drawn per sample
+    // from a counter-based generator keyed by (seed, optimiser step, sample).
+    const uint64_t st = step ? (uint64_t)*step : 0ull;
+    const Philox4 r = philox4x32_10((uint32_t)b, (uint32_t)st, (uint32_t)(st >> 32), 7u, (uint32_t)aug_seed,
+                                    (uint32_t)(aug_seed >> 32));
+    const float u0 = r.x * 2.3283064e-10f, u1 = r.y * 2.3283064e-10f, u2 = r.z * 2.3283064e-10f;
+    const float sh = (u0 * 2.f - 1.f) * 0.2f * 0.017453292f;
+    const float zx = 1.f + (u1 * 2.f - 1.f) * 0.2f, zy = 1.f + (u2 * 2.f - 1.f) * 0.2f;
+    const float flip = (r.w & 1u) ? -1.f : 1.f;
+    tl[0] = zx * flip; tl[1] = -sinf(sh) * zx; tl[2] = 0.f;
+    tl[3] = 0.f; tl[4] = cosf(sh) * zy; tl[5] = 0.f;
+    warp_img = true;
+  }
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    const int w = p % W;
+    const int h = p / W;
+    const int64_t m = (int64_t)b * HW + p;
     float c[3];
-    if (theta) {
-      const float* t = theta + b * 6;
+    if (warp_img) {
+      const float* t = tl;
       const float xn = (2.f * w + 1.f) / W - 1.f, yn = (2.f * h + 1.f) / H - 1.f;
       const float sx = t[0] * xn + t[1] * yn + t[2], sy = t[3] * xn + t[4] * yn + t[5];
       float ix = ((sx + 1.f) * W - 1.f) * 0.5f, iy = ((sy + 1.f) * H - 1.f) * 0.5f;
@@ -92,11 +114,12 @@ __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ x, const float*
   }
 }
 
-void preprocess_u8(const uint8_t* x, const float* theta, void* X, int B, int H, int W, cudaStream_t st) {
-  const int64_t P = (int64_t)B * H * W;
-  int blocks = (int)((P + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  preprocess_u8_kernel<<<blocks, 256, 0, st>>>(x, theta, reinterpret_cast<__nv_bfloat16*>(X), B, H, W);
+void preprocess_u8(const uint8_t* x, const float* theta, void* X, int B, int H, int W, uint64_t aug_seed,
+                   const int64_t* step, cudaStream_t st) {
+  int bx = (H * W + 255) / 256;
+  if (bx > 64) bx = 64;
+  dim3 grid(bx, B);
+  preprocess_u8_kernel<<<grid, 256, 0, st>>>(x, theta, reinterpret_cast<__nv_bfloat16*>(X), B, H, W, aug_seed, step);
   hefl::cuda::note_launch();
 }
 
@@ -106,16 +129,15 @@ void preprocess_u8(const uint8_t* x, const float* theta, void* X, int B, int H, 
 __global__ void unpool_relu_kernel(const __nv_bfloat16* __restrict__ g, const uint8_t* __restrict__ amax,
                                    const __nv_bfloat16* __restrict__ ypool, __nv_bfloat16* __restrict__ dY, int B,
                                    int H, int W, int Hp, int Wp, int Co) {
-  const int64_t P = (int64_t)B * H * W;
   const int groups = Co >> 3;
-  const int64_t total = P * groups;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t m = t / groups;
-    const int cg = (int)(t % groups);
-    const int w = (int)(m % W);
-    const int h = (int)((m / W) % H);
-    const int b = (int)(m / ((int64_t)W * H));
-    const int hp = h >> 1, wp = w >> 1;
+  const int row = blockIdx.y;                 // b*H + h
+  const int b = row / H, h = row - b * H;
+  const int hp = h >> 1;
+  const int per_row = W * groups;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per_row; t += gridDim.x * blockDim.x) {
+    const int w = t / groups;
+    const int cg = t - w * groups;
+    const int wp = w >> 1;
     uint4 outv = make_uint4(0u, 0u, 0u, 0u);
     if (hp < Hp && wp < Wp) {
       const int64_t o = (((int64_t)b * Hp + hp) * Wp + wp) * Co + cg * 8;
@@ -142,16 +164,15 @@ __global__ void unpool_relu_kernel(const __nv_bfloat16* __restrict__ g, const ui
       }
       outv = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
-    *reinterpret_cast<uint4*>(dY + m * Co + cg * 8) = outv;
+    *reinterpret_cast<uint4*>(dY + ((int64_t)row * W + w) * Co + cg * 8) = outv;
   }
 }
 
 void unpool_relu(const void* g, const uint8_t* amax, const void* ypool, void* dY, int B, int H, int W, int Hp,
                  int Wp, int Co, cudaStream_t st) {
-  const int64_t total = (int64_t)B * H * W * (Co / 8);
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 32) blocks = 148 * 32;
-  unpool_relu_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), amax,
+  const int per_row = W * (Co / 8);
+  dim3 grid((per_row + 255) / 256, B * H);
+  unpool_relu_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), amax,
                                              reinterpret_cast<const __nv_bfloat16*>(ypool),
                                              reinterpret_cast<__nv_bfloat16*>(dY), B, H, W, Hp, Wp, Co);
   hefl::cuda::note_launch();

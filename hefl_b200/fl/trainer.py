@@ -70,6 +70,7 @@ class LocalTrainer:
             from ..ops.conv_engine import MedCNNEngine
 
             self.engine = MedCNNEngine(model, pack, cfg, device)
+            self.engine.step_ref = self.step_t
 
     # ------------------------------------------------------------------ one step (eager)
     def _prep(self, x_u8: torch.Tensor, train: bool) -> torch.Tensor:

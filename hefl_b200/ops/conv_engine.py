@@ -91,6 +91,8 @@ class MedCNNEngine:
         self.table = torch.tensor(rows, dtype=torch.int64)
         self.bias = [pack.flat[self.b_off[l]: self.b_off[l] + self.Co[l]] for l in range(self.n)]
         self.theta = torch.zeros(B, 2, 3, dtype=torch.float32, device=device)
+        self.aug_seed = (cfg.seed * 2654435761 + 12345) & 0x7FFFFFFFFFFFFFFF or 1
+        self.step_ref: Optional[torch.Tensor] = None     # device step counter (set by the trainer)
         self.after_restore()
 
     # ------------------------------------------------------------------ weights
@@ -127,8 +129,9 @@ class MedCNNEngine:
         return th
 
     def features(self, x_u8: torch.Tensor, train: bool, augment: bool) -> torch.Tensor:
-        theta = self._make_theta() if (train and augment) else None
-        self.ops.preprocess_u8(x_u8, theta, self.X[0])
+        # augmentation parameters are drawn inside the kernel (Philox keyed by seed and step)
+        seed = self.aug_seed if (train and augment) else 0
+        self.ops.preprocess_u8(x_u8, None, self.X[0], seed, self.step_ref)
         for l in range(self.n):
             h = self.H[l]
             self.ops.conv_fwd_pool(self.X[l], self._wf(l), self.bias[l], self.X[l + 1],

@@ -120,13 +120,13 @@ def test_preprocess_matches_grid_sample():
     x = torch.randint(0, 256, (B, H, H, 3), dtype=torch.uint8, device="cuda", generator=g)
     P = B * H * H
     X = torch.zeros(P, 16, dtype=torch.bfloat16, device="cuda")
-    ops.preprocess_u8(x, None, X)
+    ops.preprocess_u8(x, None, X, 0, None)
     ref = x.float() / 255.0
     assert (X.view(B, H, H, 16)[..., :3].float() - ref).abs().max() < 4e-3
     assert float(X[:, 3:].abs().sum()) == 0.0
     theta = torch.tensor([[[0.9, 0.05, 0.0], [0.0, 1.1, 0.0]]], device="cuda").repeat(B, 1, 1)
     theta[1, 0, 0] *= -1
-    ops.preprocess_u8(x, theta.contiguous(), X)
+    ops.preprocess_u8(x, theta.contiguous(), X, 0, None)
     xr = (x.float() / 255.0).permute(0, 3, 1, 2)
     grid = F.affine_grid(theta, list(xr.shape), align_corners=False)
     ref = F.grid_sample(xr, grid, mode="bilinear", padding_mode="border", align_corners=False).permute(0, 2, 3, 1)
@@ -155,15 +155,31 @@ def test_engine_gradients_match_autograd():
     torch.cuda.synchronize()
     g_eng = pack.grad.clone()
     pack.grad.zero_()
-    xr = (x.float() / 255.0).to(torch.bfloat16).float().permute(0, 3, 1, 2)
-    logits = model(xr)
+    class RoundBF(torch.autograd.Function):   # the reference keeps activations/grads in bf16 like the engine
+        @staticmethod
+        def forward(ctx, t):
+            return t.to(torch.bfloat16).float()
+
+        @staticmethod
+        def backward(ctx, gr):
+            return gr.to(torch.bfloat16).float()
+
+    h = (x.float() / 255.0).to(torch.bfloat16).float().permute(0, 3, 1, 2)
+    for l, conv in enumerate(model.convs):
+        h = RoundBF.apply(F.max_pool2d(F.relu(conv(h)), 2))
+        e = eng.X[l + 1].view(8, h.shape[2], h.shape[3], h.shape[1]).permute(0, 3, 1, 2).float()
+        assert (e - h).abs().max() <= 2.0 ** -7 * h.abs().max()
+    h = h.permute(0, 2, 3, 1).flatten(1)
+    for fc in model.fcs[:-1]:
+        h = F.relu(fc(h))
+    logits = model.fcs[-1](h)
     loss = F.cross_entropy(logits, y)
     loss.backward()
     g_ref = pack.grad.clone()
-    assert abs(float(out[0]) - float(loss)) < 2e-2
+    assert abs(float(out[0]) - float(loss.detach())) < 2e-3
     for key, shape, off, n in pack.entries:
         a, b = g_eng[off:off + n], g_ref[off:off + n]
         denom = b.abs().max().item() + 1e-6
         rel = (a - b).abs().max().item() / denom
         cos = F.cosine_similarity(a, b, dim=0).item() if b.norm() > 0 else 1.0
-        assert cos > 0.98 and rel < 0.2, (key, rel, cos)
+        assert cos > 0.99 and rel < 0.25, (key, rel, cos)

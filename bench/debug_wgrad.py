@@ -13,7 +13,7 @@ dY = torch.zeros(B, H, H, Co, dtype=torch.bfloat16, device="cuda"); dY[:, :Ho, :
 P = B * H * H
 dW32 = torch.zeros((9 * CK + 1) * Co, dtype=torch.float32, device="cuda")
 torch.cuda.synchronize()
-ops.conv_wgrad(x.view(-1, CK), dY.view(-1, Co), dW32, P, H, CK, Co)
+ops.conv_wgrad(x.view(-1, CK), dY.view(-1, Co), dW32, B, H, H, CK, Co)
 torch.cuda.synchronize()
 wref = torch.nn.grad.conv2d_weight(x[..., :Ci].float().permute(0, 3, 1, 2), (Co, Ci, 3, 3), dyv.float())
 got = dW32[: 9 * CK * Co].view(9, CK, Co)[:, :Ci, :].permute(2, 1, 0).reshape(Co, Ci, 3, 3)

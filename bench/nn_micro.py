@@ -49,7 +49,7 @@ def main():
         h = eng.H[l]
         gin = g if l == eng.n - 1 else eng.gX[l + 1]
         res[f"unpool{l}"] = timeit(lambda l=l, h=h, gin=gin: ops.unpool_relu(gin, eng.amax[l], eng.X[l + 1], eng.dY[l], B, h, h, eng.Co[l]))
-        res[f"wgrad{l}"] = timeit(lambda l=l, h=h: ops.conv_wgrad(eng.X[l], eng.dY[l], eng._dw(l), eng.P[l], h, eng.CK[l], eng.Co[l]))
+        res[f"wgrad{l}"] = timeit(lambda l=l, h=h: ops.conv_wgrad(eng.X[l], eng.dY[l], eng._dw(l), B, h, h, eng.CK[l], eng.Co[l]))
         if l > 0:
             res[f"dgrad{l}"] = timeit(lambda l=l, h=h: ops.conv_dgrad(eng.dY[l], eng._wd(l), eng.gX[l], B, h, h, eng.Co[l], eng.Ci[l]))
     res["finalize"] = timeit(lambda: ops.conv_grad_finalize(eng.dW32, eng.table, pack.grad))
@@ -62,10 +62,20 @@ def main():
         loss.backward()
         return feat.grad.to(torch.bfloat16)
     res["head(torch fwd+bwd)"] = timeit(head)
+    res["head(fused kernels)"] = timeit(lambda: ops.head_forward_backward(eng.X[eng.n], pack.flat, pack.grad, eng.head_offs, y, eng.dfeat, eng.h1_buf, eng.dh1_buf, out, B, eng.F, eng.H1, eng.H2, eng.C, True))
     m = torch.zeros_like(pack.grad); v = torch.zeros_like(pack.grad); st = torch.ones(1, dtype=torch.int64, device="cuda")
     res["adam"] = timeit(lambda: ops.adam_step_(pack.trainable(), pack.grad, m, v, eng.shadow, st, None, 1e-3, 1e-4, 0.9, 0.999, 1e-7))
     res["train_step(eager)"] = timeit(lambda: eng.train_step(x, y, out, augment=True), iters=5)
-    tot = sum(v for k, v in res.items() if k != "train_step(eager)")
+    # whole step as a CUDA graph
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        eng.train_step(x, y, out, augment=True)
+    torch.cuda.synchronize()
+    gph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gph):
+        eng.train_step(x, y, out, augment=True)
+    res["train_step(graph)"] = timeit(lambda: gph.replay(), iters=10)
+    tot = sum(v for k, v in res.items() if not k.startswith("train_step") and not k.startswith("head(torch") and not k.startswith("make_theta"))
     for k, v in res.items():
         print(f"{k:24s} {v:9.1f} us")
     print(f"{'sum of parts':24s} {tot:9.1f} us")

@@ -17,8 +17,13 @@ void adam_step(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_
 void conv_fwd_pool(const void* X, const void* Wf, const float* bias, void* out, uint8_t* argmax, int B, int H,
                    int W, int CK, int CO, cudaStream_t st);
 void conv_dgrad(const void* dY, const void* Wd, void* dX, int B, int H, int W, int CK, int CO, cudaStream_t st);
-void conv_wgrad(const void* X, const void* DY, float* dW32, int P, int W, int CK, int Co, cudaStream_t st);
+void conv_wgrad(const void* X, const void* DY, float* dW32, int B, int H, int W, int CK, int Co, cudaStream_t st);
 
+// Dense head (Flatten -> Dense/ReLU -> Dense/ReLU -> Dense -> softmax-CE) forward + backward.
+void head_forward_backward(const void* feat, const float* W1, const float* b1, const float* W2, const float* b2,
+                           const float* W3, const float* b3, const int64_t* y, float* gW1, float* gb1, float* gW2,
+                           float* gb2, float* gW3, float* gb3, void* dfeat, float* h1_buf, float* dh1_buf,
+                           float* out, int B, int F, int H1, int H2, int C, int train, cudaStream_t st);
 void umma_shift_probe(const void* A, const void* Bm, float* out, int CK, int shift_rows, int mode, cudaStream_t st);
 
 // ---- data-movement kernels around the convolutions (nn_kernels.cu) ----

@@ -100,11 +100,12 @@ void conv_dgrad(const Tensor& dY, const Tensor& Wd, Tensor dX, int64_t B, int64_
   hefl::nn::conv_dgrad(dY.data_ptr(), Wd.data_ptr(), dX.data_ptr(), (int)B, (int)H, (int)W, (int)CK, (int)CO, cur());
 }
 
-void conv_wgrad(const Tensor& X, const Tensor& DY, Tensor dW32, int64_t P, int64_t W, int64_t CK, int64_t Co) {
+void conv_wgrad(const Tensor& X, const Tensor& DY, Tensor dW32, int64_t B, int64_t H, int64_t W, int64_t CK, int64_t Co) {
   chk_bf16(X, "X"); chk_bf16(DY, "DY");
-  TORCH_CHECK(X.numel() == P * CK && DY.numel() == P * Co, "X must be [P,CK] and DY [P,Co]");
+  const int64_t P = B * H * W;
+  TORCH_CHECK(X.numel() == P * CK && DY.numel() == P * Co, "X must be [B*H*W,CK] and DY [B*H*W,Co]");
   TORCH_CHECK(dW32.is_cuda() && dW32.scalar_type() == at::kFloat && dW32.numel() >= (9 * CK + 1) * Co, "dW32 too small");
-  hefl::nn::conv_wgrad(X.data_ptr(), DY.data_ptr(), dW32.data_ptr<float>(), (int)P, (int)W, (int)CK, (int)Co, cur());
+  hefl::nn::conv_wgrad(X.data_ptr(), DY.data_ptr(), dW32.data_ptr<float>(), (int)B, (int)H, (int)W, (int)CK, (int)Co, cur());
 }
 
 void preprocess_u8(const Tensor& x, const c10::optional<Tensor>& theta, Tensor X, int64_t aug_seed,
@@ -136,6 +137,26 @@ void unpool_relu(const Tensor& g, const Tensor& amax, const Tensor& ypool, Tenso
   TORCH_CHECK(Co % 8 == 0, "Co must be a multiple of 8");
   hefl::nn::unpool_relu(g.data_ptr(), amax.data_ptr<uint8_t>(), ypool.data_ptr(), dY.data_ptr(), (int)B, (int)H,
                         (int)W, (int)Hp, (int)Wp, (int)Co, cur());
+}
+
+// flat / grad are the ParamPack buffers; offs = [W1, b1, W2, b2, W3, b3] element offsets.
+void head_forward_backward(const Tensor& feat, const Tensor& flat, Tensor grad, at::IntArrayRef offs, const Tensor& y,
+                           Tensor dfeat, Tensor h1_buf, Tensor dh1_buf, Tensor out, int64_t B, int64_t F, int64_t H1,
+                           int64_t H2, int64_t C, bool train) {
+  chk_bf16(feat, "feat"); chk_bf16(dfeat, "dfeat");
+  TORCH_CHECK(offs.size() == 6, "need six parameter offsets");
+  TORCH_CHECK(B <= 32 && B >= 1, "the head kernels handle up to 32 samples per step");
+  TORCH_CHECK(feat.numel() == B * F && dfeat.numel() == B * F, "feat/dfeat must be [B,F]");
+  TORCH_CHECK(flat.is_cuda() && flat.scalar_type() == at::kFloat && grad.scalar_type() == at::kFloat, "float32 parameter buffers required");
+  TORCH_CHECK(y.is_cuda() && y.scalar_type() == at::kLong && y.numel() == B, "labels must be int64 [B]");
+  TORCH_CHECK(h1_buf.numel() >= B * H1 && dh1_buf.numel() >= B * H1 && out.numel() >= 2, "scratch too small");
+  const float* p = flat.data_ptr<float>();
+  float* g = grad.data_ptr<float>();
+  hefl::nn::head_forward_backward(feat.data_ptr(), p + offs[0], p + offs[1], p + offs[2], p + offs[3], p + offs[4],
+                                  p + offs[5], y.data_ptr<int64_t>(), g + offs[0], g + offs[1], g + offs[2],
+                                  g + offs[3], g + offs[4], g + offs[5], dfeat.data_ptr(), h1_buf.data_ptr<float>(),
+                                  dh1_buf.data_ptr<float>(), out.data_ptr<float>(), (int)B, (int)F, (int)H1, (int)H2,
+                                  (int)C, train ? 1 : 0, cur());
 }
 
 Tensor umma_shift_probe(const Tensor& A, const Tensor& Bm, int64_t CK, int64_t shift_rows, int64_t mode) {
@@ -177,9 +198,10 @@ TORCH_LIBRARY_FRAGMENT(hefl, m) {
   m.def("gather_h2d_(Tensor(a!) dst, Tensor src, Tensor indices) -> ()", &gather_h2d_);
   m.def("conv_fwd_pool(Tensor X, Tensor Wf, Tensor bias, Tensor(a!) out, Tensor(b!)? argmax, int B, int H, int W, int CK, int CO) -> ()", &conv_fwd_pool);
   m.def("conv_dgrad(Tensor dY, Tensor Wd, Tensor(a!) dX, int B, int H, int W, int CK, int CO) -> ()", &conv_dgrad);
-  m.def("conv_wgrad(Tensor X, Tensor DY, Tensor(a!) dW32, int P, int W, int CK, int Co) -> ()", &conv_wgrad);
+  m.def("conv_wgrad(Tensor X, Tensor DY, Tensor(a!) dW32, int B, int H, int W, int CK, int Co) -> ()", &conv_wgrad);
   m.def("preprocess_u8(Tensor x, Tensor? theta, Tensor(a!) X, int aug_seed, Tensor? step) -> ()", &preprocess_u8);
   m.def("unpool_relu(Tensor g, Tensor amax, Tensor ypool, Tensor(a!) dY, int B, int H, int W, int Co) -> ()", &unpool_relu);
+  m.def("head_forward_backward(Tensor feat, Tensor flat, Tensor(a!) grad, int[] offs, Tensor y, Tensor(b!) dfeat, Tensor(c!) h1_buf, Tensor(d!) dh1_buf, Tensor(e!) out, int B, int F, int H1, int H2, int C, bool train) -> ()", &head_forward_backward);
   m.def("umma_shift_probe(Tensor A, Tensor Bm, int CK, int shift_rows, int mode) -> Tensor", &umma_shift_probe);
   m.def("conv_weight_relayout(Tensor shadow, Tensor table, Tensor(a!) Wf, Tensor(b!) Wd) -> ()", &conv_weight_relayout);
   m.def("conv_grad_finalize(Tensor(a!) dW32, Tensor table, Tensor(b!) grad) -> ()", &conv_grad_finalize);

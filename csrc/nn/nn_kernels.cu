@@ -129,52 +129,61 @@ void preprocess_u8(const uint8_t* x, const float* theta, void* X, int B, int H, 
 __global__ void unpool_relu_kernel(const __nv_bfloat16* __restrict__ g, const uint8_t* __restrict__ amax,
                                    const __nv_bfloat16* __restrict__ ypool, __nv_bfloat16* __restrict__ dY, int B,
                                    int H, int W, int Hp, int Wp, int Co) {
+  // One thread = one 2x2 window x 8 channels: reads the pooled data once, writes all four
+  // positions (windows outside the pooled grid write zeros so the whole H x W grid is defined).
   const int groups = Co >> 3;
-  const int row = blockIdx.y;                 // b*H + h
-  const int b = row / H, h = row - b * H;
-  const int hp = h >> 1;
-  const int per_row = W * groups;
+  const int Wh = (W + 1) >> 1;
+  const int rowp = blockIdx.y;                // b*Hh + hh, Hh = ceil(H/2)
+  const int Hh = (H + 1) >> 1;
+  const int b = rowp / Hh, hh = rowp - b * Hh;
+  const int per_row = Wh * groups;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per_row; t += gridDim.x * blockDim.x) {
-    const int w = t / groups;
-    const int cg = t - w * groups;
-    const int wp = w >> 1;
-    uint4 outv = make_uint4(0u, 0u, 0u, 0u);
-    if (hp < Hp && wp < Wp) {
-      const int64_t o = (((int64_t)b * Hp + hp) * Wp + wp) * Co + cg * 8;
+    const int ww = t / groups;
+    const int cg = t - ww * groups;
+    uint32_t ow[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ow[q][i] = 0u;
+    if (hh < Hp && ww < Wp) {
+      const int64_t o = (((int64_t)b * Hp + hh) * Wp + ww) * Co + cg * 8;
       const uint4 gv = *reinterpret_cast<const uint4*>(g + o);
       const uint4 yv = *reinterpret_cast<const uint4*>(ypool + o);
       const uint2 av = *reinterpret_cast<const uint2*>(amax + o);
-      const uint32_t pos = (uint32_t)((h & 1) * 2 + (w & 1));
       const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
       const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
       const uint32_t aw[2] = {av.x, av.y};
-      uint32_t ow[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        uint32_t r = 0;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int c = i * 2 + j;
-          const uint32_t a8 = (aw[c >> 2] >> ((c & 3) * 8)) & 0xFFu;
+          const uint32_t a8 = (aw[c >> 2] >> ((c & 3) * 8)) & 3u;
           const uint32_t yb = (yw[i] >> (16 * j)) & 0xFFFFu;
-          const bool on = a8 == pos && yb != 0u && (yb & 0x8000u) == 0u;   // pooled > 0
-          if (on) r |= ((gw[i] >> (16 * j)) & 0xFFFFu) << (16 * j);
+          const bool on = yb != 0u && (yb & 0x8000u) == 0u;             // pooled > 0
+          const uint32_t val = on ? (((gw[i] >> (16 * j)) & 0xFFFFu) << (16 * j)) : 0u;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ow[q][i] |= (a8 == (uint32_t)q) ? val : 0u;
         }
-        ow[i] = r;
       }
-      outv = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
-    *reinterpret_cast<uint4*>(dY + ((int64_t)row * W + w) * Co + cg * 8) = outv;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int h = 2 * hh + (q >> 1), w = 2 * ww + (q & 1);
+      if (h < H && w < W)
+        *reinterpret_cast<uint4*>(dY + (((int64_t)b * H + h) * W + w) * Co + cg * 8) =
+            make_uint4(ow[q][0], ow[q][1], ow[q][2], ow[q][3]);
+    }
   }
 }
 
 void unpool_relu(const void* g, const uint8_t* amax, const void* ypool, void* dY, int B, int H, int W, int Hp,
                  int Wp, int Co, cudaStream_t st) {
-  const int per_row = W * (Co / 8);
-  dim3 grid((per_row + 255) / 256, B * H);
-  unpool_relu_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), amax,
-                                             reinterpret_cast<const __nv_bfloat16*>(ypool),
-                                             reinterpret_cast<__nv_bfloat16*>(dY), B, H, W, Hp, Wp, Co);
+  const int per_row = ((W + 1) / 2) * (Co / 8);
+  dim3 grid((per_row + 127) / 128, B * ((H + 1) / 2));
+  unpool_relu_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), amax,
+                                           reinterpret_cast<const __nv_bfloat16*>(ypool),
+                                           reinterpret_cast<__nv_bfloat16*>(dY), B, H, W, Hp, Wp, Co);
   hefl::cuda::note_launch();
 }
 
@@ -233,6 +242,240 @@ void conv_grad_finalize(float* dW32, const ConvLayerTable& t, float* grad, cudaS
   const int64_t total = t.dw_off[l] + (int64_t)(9 * t.CK[l] + 1) * t.Co[l];
   zero_f32_kernel<<<64, 256, 0, st>>>(dW32, total);
   hefl::cuda::note_launch(2);
+}
+
+}  // namespace nn
+}  // namespace hefl
+
+// ------------------------------------------------------------------------------------------
+// Dense head of the sequential CNNs: Flatten -> Dense(H1, ReLU) -> Dense(H2, ReLU) -> Dense(C)
+// -> softmax cross-entropy (FLPyfhelin.py:133-136, :141), forward AND backward in three launches
+// (K16/K17). The head is ~13 MFLOP at batch 32: latency-, not throughput-bound, so plain fp32
+// CUDA-core kernels with shared-memory staging beat a chain of ~30 library kernels.
+// ------------------------------------------------------------------------------------------
+namespace hefl {
+namespace nn {
+
+// h1[b][j] = relu(b1[j] + sum_k feat[b][k] * W1[j][k]). One CTA = 8 neurons; thread = (sample, neuron);
+// both operands are staged in shared memory (coalesced loads), 4 independent accumulators per thread.
+__global__ void __launch_bounds__(256)
+head_fc1_fwd_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict__ W1,
+                    const float* __restrict__ b1, float* __restrict__ h1, int B, int F, int H1) {
+  extern __shared__ float sm1[];
+  const int FP = F + 1;
+  float* fs = sm1;                 // [B][F+1]
+  float* ws = fs + B * FP;         // [8][F+1]
+  const int j0 = blockIdx.x * 8;
+  for (int i = threadIdx.x; i < B * F; i += blockDim.x) {
+    const int b = i / F, k = i - b * F;
+    fs[b * FP + k] = __bfloat162float(feat[i]);
+  }
+  for (int i = threadIdx.x; i < 8 * F; i += blockDim.x) {
+    const int jj = i / F, k = i - jj * F;
+    ws[jj * FP + k] = (j0 + jj) < H1 ? W1[(size_t)(j0 + jj) * F + k] : 0.f;
+  }
+  __syncthreads();
+  const int b = threadIdx.x >> 3, jj = threadIdx.x & 7;
+  if (b < B && j0 + jj < H1) {
+    const float* fr = fs + b * FP;
+    const float* wr = ws + jj * FP;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int k = 0;
+    for (; k + 4 <= F; k += 4) {
+      a0 = fmaf(fr[k], wr[k], a0);
+      a1 = fmaf(fr[k + 1], wr[k + 1], a1);
+      a2 = fmaf(fr[k + 2], wr[k + 2], a2);
+      a3 = fmaf(fr[k + 3], wr[k + 3], a3);
+    }
+    for (; k < F; ++k) a0 = fmaf(fr[k], wr[k], a0);
+    const float acc = (a0 + a1) + (a2 + a3) + b1[j0 + jj];
+    h1[b * H1 + j0 + jj] = acc > 0.f ? acc : 0.f;
+  }
+}
+
+struct HeadMidArgs {
+  const float* h1;      // [B][H1]
+  const float *W2, *b2, *W3, *b3;
+  const int64_t* y;     // [B]
+  float *gW2, *gb2, *gW3, *gb3;
+  float* dh1;           // [B][H1] out
+  float* out;           // [2]: loss, ncorrect
+  int B, H1, H2, C, train;
+};
+
+__global__ void __launch_bounds__(1024)
+head_mid_kernel(const HeadMidArgs a) {
+  extern __shared__ float sm[];
+  const int B = a.B, H1 = a.H1, H2 = a.H2, C = a.C;
+  float* h1 = sm;                       // [B][H1+1]
+  float* W2 = h1 + B * (H1 + 1);        // [H2][H1+1]
+  float* h2 = W2 + H2 * (H1 + 1);       // [B][H2+1]
+  float* dh2 = h2 + B * (H2 + 1);       // [B][H2+1]
+  float* lg = dh2 + B * (H2 + 1);       // [B][C]  logits -> dlogits
+  float* red = lg + B * C;              // [2*B]
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < B * H1; i += nt) h1[(i / H1) * (H1 + 1) + i % H1] = a.h1[i];
+  for (int i = tid; i < H2 * H1; i += nt) W2[(i / H1) * (H1 + 1) + i % H1] = a.W2[i];
+  __syncthreads();
+  for (int o = tid; o < B * H2; o += nt) {                     // fc2
+    const int b = o / H2, j = o % H2;
+    float a0 = a.b2[j], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const float* hr = h1 + b * (H1 + 1);
+    const float* wr = W2 + j * (H1 + 1);
+    int i = 0;
+    for (; i + 4 <= H1; i += 4) {
+      a0 = fmaf(hr[i], wr[i], a0); a1 = fmaf(hr[i + 1], wr[i + 1], a1);
+      a2 = fmaf(hr[i + 2], wr[i + 2], a2); a3 = fmaf(hr[i + 3], wr[i + 3], a3);
+    }
+    for (; i < H1; ++i) a0 = fmaf(hr[i], wr[i], a0);
+    const float acc = (a0 + a1) + (a2 + a3);
+    h2[b * (H2 + 1) + j] = acc > 0.f ? acc : 0.f;
+  }
+  __syncthreads();
+  for (int o = tid; o < B * C; o += nt) {                      // fc3
+    const int b = o / C, c = o % C;
+    float acc = a.b3[c];
+    for (int j = 0; j < H2; ++j) acc = fmaf(h2[b * (H2 + 1) + j], a.W3[c * H2 + j], acc);
+    lg[o] = acc;
+  }
+  __syncthreads();
+  if (tid < B) {                                               // softmax cross-entropy per sample
+    float mx = -1e30f;
+    int am = 0;
+    for (int c = 0; c < C; ++c) if (lg[tid * C + c] > mx) { mx = lg[tid * C + c]; am = c; }
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += __expf(lg[tid * C + c] - mx);
+    const int yy = (int)a.y[tid];
+    red[tid] = -(lg[tid * C + yy] - mx - __logf(s));
+    red[B + tid] = am == yy ? 1.f : 0.f;
+    const float invB = 1.f / B;
+    for (int c = 0; c < C; ++c) {
+      const float p = __expf(lg[tid * C + c] - mx) / s;
+      lg[tid * C + c] = (p - (c == yy ? 1.f : 0.f)) * invB;   // dlogits
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float l = 0.f, nc = 0.f;
+    for (int b = 0; b < B; ++b) { l += red[b]; nc += red[B + b]; }
+    a.out[0] = l / B;
+    a.out[1] = nc;
+  }
+  if (!a.train) return;
+  for (int o = tid; o < C * H2 + C; o += nt) {                 // dW3, db3
+    if (o < C * H2) {
+      const int c = o / H2, j = o % H2;
+      float acc = 0.f;
+      for (int b = 0; b < B; ++b) acc = fmaf(lg[b * C + c], h2[b * (H2 + 1) + j], acc);
+      a.gW3[o] = acc;
+    } else {
+      const int c = o - C * H2;
+      float acc = 0.f;
+      for (int b = 0; b < B; ++b) acc += lg[b * C + c];
+      a.gb3[c] = acc;
+    }
+  }
+  for (int o = tid; o < B * H2; o += nt) {                     // dh2
+    const int b = o / H2, j = o % H2;
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) acc = fmaf(lg[b * C + c], a.W3[c * H2 + j], acc);
+    dh2[b * (H2 + 1) + j] = h2[b * (H2 + 1) + j] > 0.f ? acc : 0.f;
+  }
+  __syncthreads();
+  for (int o = tid; o < H2 * H1 + H2; o += nt) {               // dW2, db2
+    if (o < H2 * H1) {
+      const int j = o / H1, i = o % H1;
+      float a0 = 0.f, a1 = 0.f;
+      int b = 0;
+      for (; b + 2 <= B; b += 2) {
+        a0 = fmaf(dh2[b * (H2 + 1) + j], h1[b * (H1 + 1) + i], a0);
+        a1 = fmaf(dh2[(b + 1) * (H2 + 1) + j], h1[(b + 1) * (H1 + 1) + i], a1);
+      }
+      for (; b < B; ++b) a0 = fmaf(dh2[b * (H2 + 1) + j], h1[b * (H1 + 1) + i], a0);
+      a.gW2[o] = a0 + a1;
+    } else {
+      const int j = o - H2 * H1;
+      float acc = 0.f;
+      for (int b = 0; b < B; ++b) acc += dh2[b * (H2 + 1) + j];
+      a.gb2[j] = acc;
+    }
+  }
+  for (int o = tid; o < B * H1; o += nt) {                     // dh1
+    const int b = o / H1, i = o % H1;
+    float a0 = 0.f, a1 = 0.f;
+    int j = 0;
+    for (; j + 2 <= H2; j += 2) {
+      a0 = fmaf(dh2[b * (H2 + 1) + j], W2[j * (H1 + 1) + i], a0);
+      a1 = fmaf(dh2[b * (H2 + 1) + j + 1], W2[(j + 1) * (H1 + 1) + i], a1);
+    }
+    for (; j < H2; ++j) a0 = fmaf(dh2[b * (H2 + 1) + j], W2[j * (H1 + 1) + i], a0);
+    a.dh1[o] = h1[b * (H1 + 1) + i] > 0.f ? (a0 + a1) : 0.f;
+  }
+}
+
+// dW1[j][k] = sum_b dh1[b][j] feat[b][k]; db1[j] = sum_b dh1[b][j]; dfeat[b][k] = sum_j dh1[b][j] W1[j][k].
+// One CTA owns 16 input columns k.
+__global__ void __launch_bounds__(256)
+head_fc1_bwd_kernel(const float* __restrict__ dh1, const __nv_bfloat16* __restrict__ feat,
+                    const float* __restrict__ W1, float* __restrict__ gW1, float* __restrict__ gb1,
+                    __nv_bfloat16* __restrict__ dfeat, int B, int F, int H1) {
+  extern __shared__ float sm[];
+  float* d = sm;                       // [B][H1+1]
+  float* fs = d + B * (H1 + 1);        // [B][16]
+  float* ws = fs + B * 16;             // [H1][17]
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int k0 = blockIdx.x * 16;
+  for (int i = tid; i < B * H1; i += nt) d[(i / H1) * (H1 + 1) + i % H1] = dh1[i];
+  for (int i = tid; i < B * 16; i += nt) {
+    const int b = i >> 4, k = i & 15;
+    fs[i] = k0 + k < F ? __bfloat162float(feat[b * F + k0 + k]) : 0.f;
+  }
+  for (int i = tid; i < H1 * 16; i += nt) {
+    const int j = i >> 4, k = i & 15;
+    ws[j * 17 + k] = k0 + k < F ? W1[(size_t)j * F + k0 + k] : 0.f;
+  }
+  __syncthreads();
+  for (int o = tid; o < H1 * 16; o += nt) {
+    const int j = o >> 4, k = o & 15;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc = fmaf(d[b * (H1 + 1) + j], fs[b * 16 + k], acc);
+    if (k0 + k < F) gW1[(size_t)j * F + k0 + k] = acc;
+  }
+  for (int o = tid; o < B * 16; o += nt) {
+    const int b = o >> 4, k = o & 15;
+    float acc = 0.f;
+    for (int j = 0; j < H1; ++j) acc = fmaf(d[b * (H1 + 1) + j], ws[j * 17 + k], acc);
+    if (k0 + k < F) dfeat[b * F + k0 + k] = __float2bfloat16(acc);
+  }
+  if (blockIdx.x == 0) {
+    for (int j = tid; j < H1; j += nt) {
+      float acc = 0.f;
+      for (int b = 0; b < B; ++b) acc += d[b * (H1 + 1) + j];
+      gb1[j] = acc;
+    }
+  }
+}
+
+void head_forward_backward(const void* feat, const float* W1, const float* b1, const float* W2, const float* b2,
+                           const float* W3, const float* b3, const int64_t* y, float* gW1, float* gb1, float* gW2,
+                           float* gb2, float* gW3, float* gb3, void* dfeat, float* h1_buf, float* dh1_buf,
+                           float* out, int B, int F, int H1, int H2, int C, int train, cudaStream_t st) {
+  const auto* f = reinterpret_cast<const __nv_bfloat16*>(feat);
+  const int smem_a = (B + 8) * (F + 1) * 4;
+  cudaFuncSetAttribute(head_fc1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
+  head_fc1_fwd_kernel<<<(H1 + 7) / 8, 256, smem_a, st>>>(f, W1, b1, h1_buf, B, F, H1);
+  HeadMidArgs a{h1_buf, W2, b2, W3, b3, y, gW2, gb2, gW3, gb3, dh1_buf, out, B, H1, H2, C, train};
+  const int smem_b = (B * (H1 + 1) + H2 * (H1 + 1) + 2 * B * (H2 + 1) + B * C + 2 * B) * 4;
+  cudaFuncSetAttribute(head_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
+  head_mid_kernel<<<1, 1024, smem_b, st>>>(a);
+  hefl::cuda::note_launch(2);
+  if (train) {
+    const int smem_c = (B * (H1 + 1) + B * 16 + H1 * 17) * 4;
+    cudaFuncSetAttribute(head_fc1_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c);
+    head_fc1_bwd_kernel<<<(F + 15) / 16, 256, smem_c, st>>>(dh1_buf, f, W1, gW1, gb1,
+                                                            reinterpret_cast<__nv_bfloat16*>(dfeat), B, F, H1);
+    hefl::cuda::note_launch();
+  }
 }
 
 }  // namespace nn

@@ -52,11 +52,13 @@ BINDING_SOURCES = [
 ]
 
 
-def _headers_digest() -> str:
+def _headers_digest(subdirs) -> str:
+    """Digest of the headers a source directory can see: its own plus csrc/he (shared arithmetic)."""
     h = hashlib.sha256()
-    for p in sorted(CSRC.rglob("*")):
-        if p.suffix in (".h", ".cuh", ".hpp"):
-            h.update(p.read_bytes())
+    for sub in sorted(set(subdirs) | {"he"}):
+        for p in sorted((CSRC / sub).rglob("*")):
+            if p.suffix in (".h", ".cuh", ".hpp"):
+                h.update(p.read_bytes())
     return h.hexdigest()
 
 
@@ -87,7 +89,14 @@ def build(verbose: bool = True, force: bool = False) -> Path:
     """Compile every source (if stale) and link ``_native.so``. Returns its path."""
     OBJ_DIR.mkdir(exist_ok=True)
     inc, abi, torch_lib = _torch_flags()
-    hdr = _headers_digest()
+    hdr_cache = {}
+
+    def hdr_for(src: Path) -> str:
+        sub = src.relative_to(CSRC).parts[0]
+        if sub not in hdr_cache:
+            hdr_cache[sub] = _headers_digest([sub])
+        return hdr_cache[sub]
+
     cuda_inc = "/usr/local/cuda/include"
     jobs = []
     objs = []
@@ -96,7 +105,7 @@ def build(verbose: bool = True, force: bool = False) -> Path:
     def digest_for(src: Path, flags: list[str]) -> str:
         h = hashlib.sha256()
         h.update(src.read_bytes())
-        h.update(hdr.encode())
+        h.update(hdr_for(src).encode())
         # include paths differ between the CPU box and the GPU box; they do not change the object
         h.update(" ".join(f for f in flags if not f.startswith("-I")).encode())
         return h.hexdigest()

@@ -64,7 +64,9 @@ class MedCNNEngine:
         bf = dict(dtype=torch.bfloat16, device=device)
         self.P = [B * self.H[l] * self.H[l] for l in range(self.n + 1)]
         # activations / gradients (all NHWC bf16 viewed as [pixels, channels])
-        self.X = [torch.zeros(self.P[0], 16, **bf)]
+        # layer-1 input with 8 pixels of slack: its wgrad reads 4-pixel windows (overlapping TMA rows)
+        self._x0_base = torch.zeros(self.P[0] + 8, 16, **bf)
+        self.X = [self._x0_base[: self.P[0]]]
         self.amax, self.dY, self.gX = [], [], [None]
         for l in range(self.n):
             hp = self.H[l + 1]
@@ -90,6 +92,18 @@ class MedCNNEngine:
             self.b_off.append(offs[kb])
         self.table = torch.tensor(rows, dtype=torch.int64)
         self.bias = [pack.flat[self.b_off[l]: self.b_off[l] + self.Co[l]] for l in range(self.n)]
+        # dense head: fused kernels when it is the reference's 3-layer shape, else PyTorch autograd
+        fcs = list(model.fcs)
+        self.fused_head = len(fcs) == 3 and B <= 32
+        if self.fused_head:
+            nfc = self.n * 2 + 1
+            self.head_offs = []
+            for i in range(3):
+                self.head_offs += [offs[f"c_{nfc + i}_0"], offs[f"c_{nfc + i}_1"]]
+            self.F, self.H1, self.H2, self.C = fcs[0].in_features, fcs[0].out_features, fcs[1].out_features, fcs[2].out_features
+            self.h1_buf = torch.zeros(B * self.H1, dtype=torch.float32, device=device)
+            self.dh1_buf = torch.zeros(B * self.H1, dtype=torch.float32, device=device)
+            self.dfeat = torch.zeros(B, self.F, **bf)
         self.theta = torch.zeros(B, 2, 3, dtype=torch.float32, device=device)
         self.aug_seed = (cfg.seed * 2654435761 + 12345) & 0x7FFFFFFFFFFFFFFF or 1
         self.step_ref: Optional[torch.Tensor] = None     # device step counter (set by the trainer)
@@ -148,24 +162,34 @@ class MedCNNEngine:
     # ------------------------------------------------------------------ steps
     def train_step(self, x_u8: torch.Tensor, y: torch.Tensor, out: torch.Tensor, augment: bool = True) -> None:
         feat_bf = self.features(x_u8, True, augment)
-        feat = feat_bf.view(self.B, -1).float().requires_grad_(True)
-        logits = self._head(feat)
-        loss = F.cross_entropy(logits, y)
-        loss.backward()
-        out[0] = loss.detach()
-        out[1] = (logits.argmax(1) == y).sum()
-        g = feat.grad.to(torch.bfloat16).view_as(feat_bf).contiguous()
+        if self.fused_head:
+            self.ops.head_forward_backward(feat_bf, self.pack.flat, self.pack.grad, self.head_offs, y, self.dfeat,
+                                           self.h1_buf, self.dh1_buf, out, self.B, self.F, self.H1, self.H2, self.C, True)
+            g = self.dfeat.view_as(feat_bf)
+        else:
+            feat = feat_bf.view(self.B, -1).float().requires_grad_(True)
+            logits = self._head(feat)
+            loss = F.cross_entropy(logits, y)
+            loss.backward()
+            out[0] = loss.detach()
+            out[1] = (logits.argmax(1) == y).sum()
+            g = feat.grad.to(torch.bfloat16).view_as(feat_bf).contiguous()
         for l in range(self.n - 1, -1, -1):
             h = self.H[l]
             self.ops.unpool_relu(g, self.amax[l], self.X[l + 1], self.dY[l], self.B, h, h, self.Co[l])
-            self.ops.conv_wgrad(self.X[l], self.dY[l], self._dw(l), self.P[l], h, self.CK[l], self.Co[l])
+            self.ops.conv_wgrad(self.X[l], self.dY[l], self._dw(l), self.B, h, h, self.CK[l], self.Co[l])
             if l > 0:
                 self.ops.conv_dgrad(self.dY[l], self._wd(l), self.gX[l], self.B, h, h, self.Co[l], self.Ci[l])
                 g = self.gX[l]
         self.ops.conv_grad_finalize(self.dW32, self.table, self.pack.grad)
 
     def eval_step(self, x_u8: torch.Tensor, y: torch.Tensor, out: torch.Tensor) -> None:
-        feat = self.features(x_u8, False, False).view(self.B, -1).float()
+        feat_bf = self.features(x_u8, False, False)
+        if self.fused_head:
+            self.ops.head_forward_backward(feat_bf, self.pack.flat, self.pack.grad, self.head_offs, y, self.dfeat,
+                                           self.h1_buf, self.dh1_buf, out, self.B, self.F, self.H1, self.H2, self.C, False)
+            return
+        feat = feat_bf.view(self.B, -1).float()
         logits = self._head(feat)
         out[0] = F.cross_entropy(logits, y)
         out[1] = (logits.argmax(1) == y).sum()

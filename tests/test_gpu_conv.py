@@ -15,11 +15,13 @@ def _bf(x):
 
 def _rand_layer(B, H, Ci, CK, Co, seed):
     g = torch.Generator(device="cuda").manual_seed(seed)
-    x = torch.zeros(B, H, H, CK, device="cuda")
+    base = torch.zeros(B * H * H + 8, CK, device="cuda")          # slack: layer-1 wgrad reads 4-pixel windows
+    x = base[: B * H * H].view(B, H, H, CK)
     x[..., :Ci] = torch.randn(B, H, H, Ci, device="cuda", generator=g)
     w = torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) * (1.0 / (3 * Ci ** 0.5))
     b = torch.randn(Co, device="cuda", generator=g) * 0.1
-    return _bf(x), _bf(w), b
+    xb = _bf(base)[: B * H * H].view(B, H, H, CK)
+    return xb, _bf(w), b
 
 
 def _wf(w, CK):
@@ -82,7 +84,7 @@ def test_conv_wgrad_matches_torch(B, H, Ci, CK, Co):
     dY[:, :Ho, :Ho, :] = dyv.permute(0, 2, 3, 1)
     P = B * H * H
     dW32 = torch.zeros((9 * CK + 1) * Co, dtype=torch.float32, device="cuda")
-    ops.conv_wgrad(x.view(-1, CK), dY.view(-1, Co), dW32, P, H, CK, Co)
+    ops.conv_wgrad(x.view(-1, CK), dY.view(-1, Co), dW32, B, H, H, CK, Co)
     torch.cuda.synchronize()
     xr = x[..., :Ci].float().permute(0, 3, 1, 2).requires_grad_(False)
     wref = torch.nn.grad.conv2d_weight(xr, (Co, Ci, 3, 3), dyv.float())

@@ -418,11 +418,15 @@ struct WgradArgs {
   int rsplit;       // row ranges per (image, strip)
   int rows_per;     // rows per range
   int units;        // B * strips * rsplit
+  int nchunks;      // FLAT: ceil(B*H*W / 64)
   int Co;           // total output channels (row pitch of dW32)
   float* dW32;      // [9*CK + 1][Co] fp32, accumulated with vector RED
 };
 
-template <int CK, int COT>
+// FLAT = small feature maps (W <= 32): a 64-pixel chunk of one image row would be mostly padding, so
+// chunks are 64 consecutive pixels of the flattened [B*H*W] axis and each stage carries its own
+// three X segments (rows offset by W); no ring reuse, L2 traffic is irrelevant at these sizes.
+template <int CK, int COT, bool FLAT = false>
 struct WgradCfg {
   // CK = 16 (layer 1): 32-byte MN-major atoms make the tensor core read shared memory 32 bytes at
   // a time (measured ~128 cycles per MMA). Instead the X tensor map uses OVERLAPPING rows: row m is
@@ -437,10 +441,12 @@ struct WgradCfg {
   static constexpr int XROWS = PACK4 ? 64 : 72;                // 64 + pixel shifts (none when packed)
   static constexpr int A_LBO = PACK4 ? 0 : CK * 2;             // next atom = next pixel (packed: rows 64.. unused)
   static constexpr int X_BYTES = XROWS * ATOM_A;
+  static constexpr int X_SEG = ((X_BYTES + 1023) / 1024) * 1024;
   static constexpr int DY_BYTES = 64 * ATOM_B;
-  static constexpr int STAGE = ((X_BYTES + DY_BYTES + 1023) / 1024) * 1024;
-  static constexpr int DY_OFF = ((X_BYTES + 1023) / 1024) * 1024;
+  static constexpr int DY_OFF = FLAT ? 3 * X_SEG : X_SEG;
+  static constexpr int TX = (FLAT ? 3 : 1) * X_BYTES + DY_BYTES;
   static constexpr int STAGE_FULL = DY_OFF + ((DY_BYTES + 1023) / 1024) * 1024;
+  static_assert(!(FLAT && PACK4), "layer 1 always uses the rolling-window path");
   static constexpr int ONES_BYTES = 16 * 1024;                 // [128 x 64] bf16 of 1.0
   // deep ring: stages are small (one X row segment + one dY chunk), so the number of bytes in
   // flight, not the MMA rate, bounds throughput (measured: 6 stages -> 204 us on layer 1)
@@ -455,11 +461,11 @@ struct WgradCfg {
   static_assert(COT == 32 || COT == 64, "COT must be one swizzle atom");
 };
 
-template <int CK, int COT>
+template <int CK, int COT, bool FLAT>
 __global__ void __launch_bounds__(192, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
              const WgradArgs a) {
-  using Cfg = WgradCfg<CK, COT>;
+  using Cfg = WgradCfg<CK, COT, FLAT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ones = smem + Cfg::NSTAGE * Cfg::STAGE_FULL;
@@ -490,7 +496,20 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   const int per_img = a.strips * a.rsplit;
 
   if (warp == 4) {
-    if (elect_one()) {
+    if (FLAT) {
+      if (elect_one()) {
+        int slot = 0;
+        uint32_t phase = 0;
+        for (int c = blockIdx.x; c < a.nchunks; c += gridDim.x) {
+          mbar_wait(&empty[slot], phase ^ 1u);
+          uint8_t* st = smem + slot * Cfg::STAGE_FULL;
+          mbar_expect_tx(&full[slot], Cfg::TX);
+          for (int r = 0; r < 3; ++r) tma_load_2d(st + r * Cfg::X_SEG, &tmX, 0, c * 64 + r * a.W, &full[slot]);
+          tma_load_2d(st + Cfg::DY_OFF, &tmDY, co0, c * 64, &full[slot]);
+          if (++slot == Cfg::NSTAGE) { slot = 0; phase ^= 1; }
+        }
+      }
+    } else if (elect_one()) {
       int slot = 0;
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
@@ -523,7 +542,35 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     int slot = 0;                                                     // ring position of the current stage
     uint32_t phase = 0;
     uint32_t first = 1;
-    for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
+    if (FLAT) {
+      for (int c = blockIdx.x; c < a.nchunks; c += gridDim.x) {
+        mbar_wait(&full[slot], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t st_lo = smem_lo + slot * stage16;
+          const uint32_t dy_lo = st_lo + (Cfg::DY_OFF >> 4) + b_lbo;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t blo = dy_lo + ((k * 16 * Cfg::ATOM_B) >> 4);
+            const uint32_t accum = k == 0 ? (first ^ 1u) : 1u;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+              for (int mm = 0; mm < Cfg::MMA_PER_R; ++mm)
+                umma_bf16_lh(tmem_base + (r * Cfg::MMA_PER_R + mm) * COT,
+                             st_lo + a_lbo + ((r * Cfg::X_SEG + (mm * Cfg::TPG + k * 16) * Cfg::ATOM_A) >> 4), a_hi,
+                             blo, b_hi, idesc, accum);
+            }
+            umma_bf16_lh(tmem_base + Cfg::NACC * COT, ones_lo + ((k * 16 * 128) >> 4), o_hi, blo, b_hi, idesc, accum);
+          }
+          umma_commit(&empty[slot]);
+        }
+        __syncwarp();
+        first = 0;
+        if (++slot == Cfg::NSTAGE) { slot = 0; phase ^= 1; }
+      }
+    }
+    for (int u = FLAT ? a.units : (int)blockIdx.x; u < a.units; u += gridDim.x) {
       const int b = u / per_img;
       const int rem = u - b * per_img;
       const int strip = rem / a.rsplit;
@@ -575,7 +622,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     const int qd = warp;
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
     named_barrier_sync(2, 160);         // no polling while the main loop runs
-    if ((int)blockIdx.x < a.units) {
+    if ((int)blockIdx.x < (FLAT ? a.nchunks : a.units)) {
       tc_fence_after();
       const int row = qd * 32 + lane;                          // row inside an accumulator: s_local*CK + ci
 #pragma unroll 1
@@ -649,10 +696,10 @@ static CUtensorMap make_map_3d_strided(const void* ptr, uint64_t C, uint64_t W, 
   return m;
 }
 
-template <int CK, int COT>
+template <int CK, int COT, bool FLAT>
 static void launch_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* DY, int B, int H, int W, int Co, float* dW32,
                          cudaStream_t st) {
-  using Cfg = WgradCfg<CK, COT>;
+  using Cfg = WgradCfg<CK, COT, FLAT>;
   WgradArgs a{};
   a.H = H; a.W = W; a.Ho = H - 2;
   a.strips = (W - 2 + 63) / 64;
@@ -661,18 +708,28 @@ static void launch_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* DY, int B,
   a.rows_per = a.Ho < 16 ? a.Ho : 16;
   a.rsplit = (a.Ho + a.rows_per - 1) / a.rows_per;
   a.units = B * a.strips * a.rsplit;
+  const int P = B * H * W;
+  a.nchunks = (P + 63) / 64;
   a.Co = Co;
   a.dW32 = dW32;
-  const CUtensorMap tmX = Cfg::PACK4 ? make_map_3d_strided(X, 64, W, (uint64_t)B * H, 32, (uint64_t)W * 32, 64, Cfg::XROWS)
-                                     : make_map_3d(X, CK, W, (uint64_t)B * H, CK, Cfg::XROWS);
-  const CUtensorMap tmD = make_map_3d(DY, Co, W, (uint64_t)B * H, COT, 64);
-  auto kern = wgrad_kernel<CK, COT>;
+  CUtensorMap tmX, tmD;
+  int total_steps;
+  if (FLAT) {
+    tmX = make_map(X, CK, (uint64_t)P, (uint64_t)CK * 2, CK, Cfg::XROWS);
+    tmD = make_map(DY, Co, (uint64_t)P, (uint64_t)Co * 2, COT, 64);
+    total_steps = a.nchunks;
+  } else {
+    tmX = Cfg::PACK4 ? make_map_3d_strided(X, 64, W, (uint64_t)B * H, 32, (uint64_t)W * 32, 64, Cfg::XROWS)
+                     : make_map_3d(X, CK, W, (uint64_t)B * H, CK, Cfg::XROWS);
+    tmD = make_map_3d(DY, Co, W, (uint64_t)B * H, COT, 64);
+    total_steps = a.units * (a.rows_per + 2);
+  }
+  auto kern = wgrad_kernel<CK, COT, FLAT>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-  // every CTA pays a fixed epilogue (fp32 RED of all accumulators): give each at least ~24 steps
-  const int total_steps = a.units * (a.rows_per + 2);
-  int gx = total_steps / 24;
+  // every CTA pays a fixed epilogue (fp32 RED of all accumulators): give each at least a few steps
+  int gx = total_steps / (FLAT ? 6 : 24);
   if (gx > num_sms() / cot) gx = num_sms() / cot;
-  if (gx > a.units) gx = a.units;
+  if (gx > (FLAT ? a.nchunks : a.units)) gx = FLAT ? a.nchunks : a.units;
   if (gx < 1) gx = 1;
   dim3 grid(gx, cot);
   kern<<<grid, 192, Cfg::SMEM, st>>>(tmX, tmD, a);
@@ -682,11 +739,11 @@ static void launch_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* DY, int B,
 void conv_wgrad(const void* X, const void* DY, float* dW32, int B, int H, int W, int CK, int Co, cudaStream_t st) {
   const auto* x = reinterpret_cast<const __nv_bfloat16*>(X);
   const auto* d = reinterpret_cast<const __nv_bfloat16*>(DY);
-  if (CK == 16 && Co == 32) launch_wgrad<16, 32>(x, d, B, H, W, Co, dW32, st);
-  else if (CK == 32 && Co == 32) launch_wgrad<32, 32>(x, d, B, H, W, Co, dW32, st);
-  else if (CK == 32 && Co == 64) launch_wgrad<32, 64>(x, d, B, H, W, Co, dW32, st);
-  else if (CK == 64 && Co == 64) launch_wgrad<64, 64>(x, d, B, H, W, Co, dW32, st);
-  else if (CK == 64 && Co == 128) launch_wgrad<64, 64>(x, d, B, H, W, Co, dW32, st);
+  const bool flat = W <= 32 && CK != 16;
+  if (CK == 16 && Co == 32) launch_wgrad<16, 32, false>(x, d, B, H, W, Co, dW32, st);
+  else if (CK == 32 && Co == 32) flat ? launch_wgrad<32, 32, true>(x, d, B, H, W, Co, dW32, st) : launch_wgrad<32, 32, false>(x, d, B, H, W, Co, dW32, st);
+  else if (CK == 32 && Co == 64) flat ? launch_wgrad<32, 64, true>(x, d, B, H, W, Co, dW32, st) : launch_wgrad<32, 64, false>(x, d, B, H, W, Co, dW32, st);
+  else if (CK == 64 && (Co == 64 || Co == 128)) flat ? launch_wgrad<64, 64, true>(x, d, B, H, W, Co, dW32, st) : launch_wgrad<64, 64, false>(x, d, B, H, W, Co, dW32, st);
   else throw std::runtime_error("conv_wgrad: unsupported (CK, Co)");
 }
 

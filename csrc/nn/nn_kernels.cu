@@ -266,13 +266,31 @@ head_fc1_fwd_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restr
   float* fs = sm1;                 // [B][F+1]
   float* ws = fs + B * FP;         // [8][F+1]
   const int j0 = blockIdx.x * 8;
-  for (int i = threadIdx.x; i < B * F; i += blockDim.x) {
-    const int b = i / F, k = i - b * F;
-    fs[b * FP + k] = __bfloat162float(feat[i]);
+  // staged with 16-byte loads, several in flight per thread (the loads, not the FMAs, set the latency)
+  const int F8 = F >> 3, F4 = F >> 2;
+  for (int b = 0; b < B; ++b) {
+    const uint4* src = reinterpret_cast<const uint4*>(feat + (size_t)b * F);
+#pragma unroll 2
+    for (int k8 = threadIdx.x; k8 < F8; k8 += blockDim.x) {
+      const uint4 v = src[k8];
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      float* dst = fs + b * FP + k8 * 8;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        dst[2 * q] = __uint_as_float(w[q] << 16);
+        dst[2 * q + 1] = __uint_as_float(w[q] & 0xFFFF0000u);
+      }
+    }
   }
-  for (int i = threadIdx.x; i < 8 * F; i += blockDim.x) {
-    const int jj = i / F, k = i - jj * F;
-    ws[jj * FP + k] = (j0 + jj) < H1 ? W1[(size_t)(j0 + jj) * F + k] : 0.f;
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const bool ok = (j0 + jj) < H1;
+    const float4* src = reinterpret_cast<const float4*>(W1 + (size_t)(ok ? j0 + jj : 0) * F);
+    for (int k4 = threadIdx.x; k4 < F4; k4 += blockDim.x) {
+      const float4 v = ok ? src[k4] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float* dst = ws + jj * FP + k4 * 4;
+      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
   }
   __syncthreads();
   const int b = threadIdx.x >> 3, jj = threadIdx.x & 7;
@@ -313,13 +331,34 @@ head_mid_kernel(const HeadMidArgs a) {
   float* dh2 = h2 + B * (H2 + 1);       // [B][H2+1]
   float* lg = dh2 + B * (H2 + 1);       // [B][C]  logits -> dlogits
   float* red = lg + B * C;              // [2*B]
+  float* W3 = red + 2 * B;              // [C][H2]
+  float* b2s = W3 + C * H2;             // [H2]
+  float* b3s = b2s + H2;                // [C]
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int i = tid; i < B * H1; i += nt) h1[(i / H1) * (H1 + 1) + i % H1] = a.h1[i];
-  for (int i = tid; i < H2 * H1; i += nt) W2[(i / H1) * (H1 + 1) + i % H1] = a.W2[i];
+  {
+    const int H14 = H1 >> 2;
+    const float4* s1 = reinterpret_cast<const float4*>(a.h1);
+    const float4* s2 = reinterpret_cast<const float4*>(a.W2);
+#pragma unroll 4
+    for (int i = tid; i < B * H14; i += nt) {
+      const float4 v = s1[i];
+      float* d = h1 + (i / H14) * (H1 + 1) + (i % H14) * 4;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+#pragma unroll 4
+    for (int i = tid; i < H2 * H14; i += nt) {
+      const float4 v = s2[i];
+      float* d = W2 + (i / H14) * (H1 + 1) + (i % H14) * 4;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    for (int i = tid; i < C * H2; i += nt) W3[i] = a.W3[i];
+    for (int i = tid; i < H2; i += nt) b2s[i] = a.b2[i];
+    for (int i = tid; i < C; i += nt) b3s[i] = a.b3[i];
+  }
   __syncthreads();
   for (int o = tid; o < B * H2; o += nt) {                     // fc2
     const int b = o / H2, j = o % H2;
-    float a0 = a.b2[j], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    float a0 = b2s[j], a1 = 0.f, a2 = 0.f, a3 = 0.f;
     const float* hr = h1 + b * (H1 + 1);
     const float* wr = W2 + j * (H1 + 1);
     int i = 0;
@@ -334,8 +373,8 @@ head_mid_kernel(const HeadMidArgs a) {
   __syncthreads();
   for (int o = tid; o < B * C; o += nt) {                      // fc3
     const int b = o / C, c = o % C;
-    float acc = a.b3[c];
-    for (int j = 0; j < H2; ++j) acc = fmaf(h2[b * (H2 + 1) + j], a.W3[c * H2 + j], acc);
+    float acc = b3s[c];
+    for (int j = 0; j < H2; ++j) acc = fmaf(h2[b * (H2 + 1) + j], W3[c * H2 + j], acc);
     lg[o] = acc;
   }
   __syncthreads();
@@ -378,7 +417,7 @@ head_mid_kernel(const HeadMidArgs a) {
   for (int o = tid; o < B * H2; o += nt) {                     // dh2
     const int b = o / H2, j = o % H2;
     float acc = 0.f;
-    for (int c = 0; c < C; ++c) acc = fmaf(lg[b * C + c], a.W3[c * H2 + j], acc);
+    for (int c = 0; c < C; ++c) acc = fmaf(lg[b * C + c], W3[c * H2 + j], acc);
     dh2[b * (H2 + 1) + j] = h2[b * (H2 + 1) + j] > 0.f ? acc : 0.f;
   }
   __syncthreads();
@@ -425,11 +464,13 @@ head_fc1_bwd_kernel(const float* __restrict__ dh1, const __nv_bfloat16* __restri
   float* ws = fs + B * 16;             // [H1][17]
   const int tid = threadIdx.x, nt = blockDim.x;
   const int k0 = blockIdx.x * 16;
+#pragma unroll 4
   for (int i = tid; i < B * H1; i += nt) d[(i / H1) * (H1 + 1) + i % H1] = dh1[i];
   for (int i = tid; i < B * 16; i += nt) {
     const int b = i >> 4, k = i & 15;
     fs[i] = k0 + k < F ? __bfloat162float(feat[b * F + k0 + k]) : 0.f;
   }
+#pragma unroll 4
   for (int i = tid; i < H1 * 16; i += nt) {
     const int j = i >> 4, k = i & 15;
     ws[j * 17 + k] = k0 + k < F ? W1[(size_t)j * F + k0 + k] : 0.f;
@@ -465,7 +506,7 @@ void head_forward_backward(const void* feat, const float* W1, const float* b1, c
   cudaFuncSetAttribute(head_fc1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
   head_fc1_fwd_kernel<<<(H1 + 7) / 8, 256, smem_a, st>>>(f, W1, b1, h1_buf, B, F, H1);
   HeadMidArgs a{h1_buf, W2, b2, W3, b3, y, gW2, gb2, gW3, gb3, dh1_buf, out, B, H1, H2, C, train};
-  const int smem_b = (B * (H1 + 1) + H2 * (H1 + 1) + 2 * B * (H2 + 1) + B * C + 2 * B) * 4;
+  const int smem_b = (B * (H1 + 1) + H2 * (H1 + 1) + 2 * B * (H2 + 1) + B * C + 2 * B + C * H2 + H2 + C) * 4;
   cudaFuncSetAttribute(head_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
   head_mid_kernel<<<1, 1024, smem_b, st>>>(a);
   hefl::cuda::note_launch(2);

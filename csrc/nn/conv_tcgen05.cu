@@ -112,6 +112,7 @@ struct TapGemmArgs {
   int num_tiles;
   int P;                // B*H*W
   int co_total;         // output channels of the layer (CO per CTA column block = blockIdx.y)
+  int dbg;              // bottleneck isolation (bench only): 1 = skip TMA data, 2 = skip MMAs, 4 = skip epilogue work
   const float* bias;    // [CO] (POOL)
   __nv_bfloat16* out;   // POOL: [B,Hp,Wp,CO]; else [P,CO]
   uint8_t* argmax;      // POOL, may be null
@@ -130,20 +131,26 @@ struct TapGemmCfg {
   static constexpr int W_SUB = CO * ROW_BYTES;
   static constexpr int W_TAP = W_SUB * NKB;
   static constexpr int W_BYTES = 9 * W_TAP;
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 384;
   static constexpr int BUDGET = 225 * 1024;
   static constexpr int NBUF_RAW = (BUDGET - W_BYTES - BAR_BYTES - 1024) / HALO;
   static constexpr int NBUF = NBUF_RAW > 8 ? 8 : NBUF_RAW;   // bytes in flight bound the small-channel layers
   static constexpr int SMEM = W_BYTES + NBUF * HALO + BAR_BYTES + 1024;
-  static constexpr int ACC_COLS = 2 * NACC * CO;          // two tile buffers
+  // TMEM tile buffers: the MMA -> epilogue -> MMA hand-off costs ~1500 cycles of mbarrier latency
+  // (measured with all work disabled: 750 cycles/tile with 2 buffers), so small-channel layers use
+  // up to 8 buffers to keep several tiles in flight.
+  static constexpr int NT_RAW = 512 / (NACC * CO);
+  static constexpr int NT = NT_RAW > 8 ? 8 : NT_RAW;
+  static constexpr int ACC_COLS = NT * NACC * CO;
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
+  static_assert(NT >= 2, "need at least two TMEM tile buffers");
   static_assert(NBUF >= 1, "halo tile does not fit in shared memory");
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
   static_assert(CO % 32 == 0 && CO <= 128, "CO must be 32, 64, 96 or 128");
 };
 
 template <int CK, int CO, bool POOL>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(608, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                 const TapGemmArgs a) {
   using Cfg = TapGemmCfg<CK, CO, POOL>;
@@ -155,28 +162,29 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* full = bars;                       // [NBUF]
   uint64_t* empty = bars + Cfg::NBUF;          // [NBUF]
   uint64_t* wfull = bars + 2 * Cfg::NBUF;      // [1]
-  uint64_t* tfull = wfull + 1;                 // [2]
-  uint64_t* tempty = tfull + 2;                // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* tfull = wfull + 1;                 // [NT]
+  uint64_t* tempty = tfull + Cfg::NT;          // [NT]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + Cfg::NT);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == 16 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmW);
-    for (int s = 0; s < Cfg::NBUF; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    // POOL: two MMA-issuing warps (one per accumulator) => 2 commits per buffer / tile
+    for (int s = 0; s < Cfg::NBUF; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], Cfg::NACC); }
     mbar_init(wfull, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    for (int i = 0; i < Cfg::NT; ++i) { mbar_init(&tfull[i], Cfg::NACC); mbar_init(&tempty[i], 16); }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 17) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == 16) {
     // ===== TMA producer =====
     if (elect_one()) {
       mbar_expect_tx(wfull, Cfg::W_BYTES);
@@ -201,17 +209,24 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           seg_stride = -a.W;                     // segment r starts at m0 - r*W - 2
         }
         mbar_wait(&empty[buf], phase ^ 1);
-        mbar_expect_tx(&full[buf], Cfg::HALO);
-        uint8_t* dst = sA + buf * Cfg::HALO;
-        for (int kb = 0; kb < Cfg::NKB; ++kb)
-          for (int sg = 0; sg < Cfg::NSEG; ++sg)
-            tma_load_2d(dst + (kb * Cfg::NSEG + sg) * Cfg::SEG_BYTES, &tmA, kb * Cfg::KB, base + sg * seg_stride,
-                        &full[buf]);
+        if (a.dbg & 1) {
+          mbar_arrive(&full[buf]);
+        } else {
+          mbar_expect_tx(&full[buf], Cfg::HALO);
+          uint8_t* dst = sA + buf * Cfg::HALO;
+          for (int kb = 0; kb < Cfg::NKB; ++kb)
+            for (int sg = 0; sg < Cfg::NSEG; ++sg)
+              tma_load_2d(dst + (kb * Cfg::NSEG + sg) * Cfg::SEG_BYTES, &tmA, kb * Cfg::KB, base + sg * seg_stride,
+                          &full[buf]);
+        }
         if (++buf == Cfg::NBUF) { buf = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 9) {
-    // ===== MMA issuer =====
+  } else if (warp == 17 || warp == 18) {
+    // ===== MMA issuers: warp 9 owns accumulator 0, warp 10 accumulator 1 (the small-N MMAs of these
+    // layers are bound by per-thread issue cost, not by the tensor core, so two issuers run in parallel)
+    const int jme = warp - 17;
+    if (jme >= Cfg::NACC) goto done_roles;
     constexpr uint32_t idesc = make_idesc_bf16(128, CO);
     mbar_wait(wfull, 0);
     tc_fence_after();
@@ -230,6 +245,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         constexpr uint32_t hi = desc_hi(8 * Cfg::ROW_BYTES, Cfg::ROW_BYTES);
 #pragma unroll
         for (int j = 0; j < Cfg::NACC; ++j) {
+          if (j != jme || (a.dbg & 2)) continue;
           const uint32_t d_tmem = tmem_base + (tb * Cfg::NACC + j) * CO;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
@@ -252,13 +268,14 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       __syncwarp();
       if (++buf == Cfg::NBUF) { buf = 0; phase ^= 1; }
-      tb ^= 1;
-      if (tb == 0) tb_phase ^= 1;
+      if (++tb == Cfg::NT) { tb = 0; tb_phase ^= 1; }
     }
   } else {
-    // ===== epilogue warps (0..7): quadrant = warp % 4, channel half = warp / 4 =====
+    // ===== epilogue warps (0..15): quadrant = warp % 4, channel slice = warp / 4 (8 channels a time).
+    // The small-channel layers are bound by the epilogue's instruction latency, so it is spread over
+    // 16 warps (measured: 8 warps x 16 channels = 55 us on layer 1).
     const int qd = warp & 3;                       // TMEM lane quadrant this warp may read
-    const int grp = warp >> 2;                     // which 16-channel slices this warp owns
+    const int grp = warp >> 2;
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
     int tb = 0;
     uint32_t tb_phase = 0;
@@ -275,24 +292,27 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int wp = col >> 1;
         const bool writer = ((lane & 1) == 0) && wp < a.Wp;
 #pragma unroll 1
-        for (int ch = grp; ch < CO / 16; ch += 2) {
-          float v0[16], v1[16];
-          tmem_ld16_nowait(tmem_base + lane_base + (tb * 2 + 0) * CO + ch * 16, v0);
-          tmem_ld16_nowait(tmem_base + lane_base + (tb * 2 + 1) * CO + ch * 16, v1);
+        for (int ch = grp; ch < ((a.dbg & 4) ? 0 : CO / 8); ch += 4) {
+          float v0[8], v1[8];
+          tmem_ld8_nowait(tmem_base + lane_base + (tb * 2 + 0) * CO + ch * 8, v0);
+          tmem_ld8_nowait(tmem_base + lane_base + (tb * 2 + 1) * CO + ch * 8, v1);
+          const float4 bA = __ldg(reinterpret_cast<const float4*>(a.bias + ch * 8));
+          const float4 bB = __ldg(reinterpret_cast<const float4*>(a.bias + ch * 8 + 4));
+          const float bias8[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
           tmem_ld_wait();
           // max over the 2x2 window on the raw accumulators (bias + ReLU commute with max)
           uint32_t vbits = 0;                                 // 1 = lower image row wins
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
+          for (int c = 0; c < 8; ++c) {
             const bool lw = v1[c] > v0[c];
             v0[c] = lw ? v1[c] : v0[c];
             vbits |= lw ? (1u << c) : 0u;
           }
           const uint32_t pvbits = __shfl_xor_sync(0xffffffffu, vbits, 1);
-          uint32_t packed[8];
-          uint32_t idx4[4] = {0u, 0u, 0u, 0u};
+          uint32_t packed[4];
+          uint32_t idx4[2] = {0u, 0u};
 #pragma unroll
-          for (int c = 0; c < 16; c += 2) {
+          for (int c = 0; c < 8; c += 2) {
             float x[2];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -301,46 +321,41 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               const bool rw = o > mine;
               const uint32_t id = rw ? (((pvbits >> (c + j)) & 1u) * 2u + 1u) : (((vbits >> (c + j)) & 1u) * 2u);
               idx4[(c + j) >> 2] |= id << (((c + j) & 3) * 8);
-              const float y = (rw ? o : mine) + __ldg(a.bias + ch * 16 + c + j);
+              const float y = (rw ? o : mine) + bias8[c + j];
               x[j] = y > 0.f ? y : 0.f;
             }
             packed[c >> 1] = pack_bf16x2(x[0], x[1]);
           }
           if (writer) {
-            const size_t o = ((size_t)(b * a.Hp + hp) * a.Wp + wp) * CO + ch * 16;
-            uint4* dst = reinterpret_cast<uint4*>(a.out + o);
-            dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-            if (a.argmax) *reinterpret_cast<uint4*>(a.argmax + o) = make_uint4(idx4[0], idx4[1], idx4[2], idx4[3]);
+            const size_t o = ((size_t)(b * a.Hp + hp) * a.Wp + wp) * CO + ch * 8;
+            *reinterpret_cast<uint4*>(a.out + o) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            if (a.argmax) *reinterpret_cast<uint2*>(a.argmax + o) = make_uint2(idx4[0], idx4[1]);
           }
         }
       } else {
         const int m = t * 128 + qd * 32 + lane;
 #pragma unroll 1
-        for (int ch = grp; ch < CO / 16; ch += 2) {
-          float v[16];
-          tmem_ld16_nowait(tmem_base + lane_base + tb * CO + ch * 16, v);
+        for (int ch = grp; ch < CO / 8; ch += 4) {
+          float v[8];
+          tmem_ld8_nowait(tmem_base + lane_base + tb * CO + ch * 8, v);
           tmem_ld_wait();
           if (m < a.P) {
-            uint32_t packed[8];
-#pragma unroll
-            for (int c = 0; c < 16; c += 2) packed[c >> 1] = pack_bf16x2(v[c], v[c + 1]);
-            uint4* dst = reinterpret_cast<uint4*>(a.out + (size_t)m * a.co_total + blockIdx.y * CO + ch * 16);
-            dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            *reinterpret_cast<uint4*>(a.out + (size_t)m * a.co_total + blockIdx.y * CO + ch * 8) =
+                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                           pack_bf16x2(v[6], v[7]));
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[tb]);
-      tb ^= 1;
-      if (tb == 0) tb_phase ^= 1;
+      if (++tb == Cfg::NT) { tb = 0; tb_phase ^= 1; }
     }
   }
+done_roles:
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 17) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
@@ -357,13 +372,17 @@ static void launch_tap_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Wt, Tap
   int gx = a.num_tiles < num_sms() / ny ? a.num_tiles : num_sms() / ny;
   if (gx < 1) gx = 1;
   dim3 grid(gx, ny);
-  kern<<<grid, 320, Cfg::SMEM, st>>>(tmA, tmW, a);
+  kern<<<grid, 608, Cfg::SMEM, st>>>(tmA, tmW, a);
   hefl::cuda::note_launch();
 }
+
+static int g_dbg = 0;
+void conv_set_debug(int mask) { g_dbg = mask; }
 
 void conv_fwd_pool(const void* X, const void* Wf, const float* bias, void* out, uint8_t* argmax, int B, int H,
                    int W, int CK, int CO, cudaStream_t st) {
   TapGemmArgs a{};
+  a.dbg = g_dbg;
   a.B = B; a.H = H; a.W = W;
   a.Hp = (H - 2) / 2; a.Wp = (W - 2) / 2;
   a.tiles_w = (2 * a.Wp + 127) / 128;

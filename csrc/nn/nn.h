@@ -16,6 +16,7 @@ void adam_step(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_
 // ---- tcgen05 implicit-GEMM convolution (conv_tcgen05.cu) ----
 void conv_fwd_pool(const void* X, const void* Wf, const float* bias, void* out, uint8_t* argmax, int B, int H,
                    int W, int CK, int CO, cudaStream_t st);
+void conv_set_debug(int mask);
 void conv_dgrad(const void* dY, const void* Wd, void* dX, int B, int H, int W, int CK, int CO, cudaStream_t st);
 void conv_wgrad(const void* X, const void* DY, float* dW32, int B, int H, int W, int CK, int Co, cudaStream_t st);
 

@@ -159,6 +159,8 @@ void head_forward_backward(const Tensor& feat, const Tensor& flat, Tensor grad, 
                                   (int)C, train ? 1 : 0, cur());
 }
 
+void conv_set_debug(int64_t mask) { hefl::nn::conv_set_debug((int)mask); }
+
 Tensor umma_shift_probe(const Tensor& A, const Tensor& Bm, int64_t CK, int64_t shift_rows, int64_t mode) {
   chk_bf16(A, "A"); chk_bf16(Bm, "Bm");
   TORCH_CHECK(A.numel() == 144 * CK && Bm.numel() == 32 * CK, "A must be [144,CK], B [32,CK]");
@@ -202,6 +204,7 @@ TORCH_LIBRARY_FRAGMENT(hefl, m) {
   m.def("preprocess_u8(Tensor x, Tensor? theta, Tensor(a!) X, int aug_seed, Tensor? step) -> ()", &preprocess_u8);
   m.def("unpool_relu(Tensor g, Tensor amax, Tensor ypool, Tensor(a!) dY, int B, int H, int W, int Co) -> ()", &unpool_relu);
   m.def("head_forward_backward(Tensor feat, Tensor flat, Tensor(a!) grad, int[] offs, Tensor y, Tensor(b!) dfeat, Tensor(c!) h1_buf, Tensor(d!) dh1_buf, Tensor(e!) out, int B, int F, int H1, int H2, int C, bool train) -> ()", &head_forward_backward);
+  m.def("conv_set_debug(int mask) -> ()", &conv_set_debug);
   m.def("umma_shift_probe(Tensor A, Tensor Bm, int CK, int shift_rows, int mode) -> Tensor", &umma_shift_probe);
   m.def("conv_weight_relayout(Tensor shadow, Tensor table, Tensor(a!) Wf, Tensor(b!) Wd) -> ()", &conv_weight_relayout);
   m.def("conv_grad_finalize(Tensor(a!) dW32, Tensor table, Tensor(b!) grad) -> ()", &conv_grad_finalize);

@@ -177,19 +177,19 @@ class LocalTrainer:
         best_loss, best_acc, wait_es, wait_lr = float("inf"), -1.0, 0, 0
         best_weights = None
         B = self.cfg.batch_size
-        pinned = self.cuda
+        lr_scale_host = float(self.lr_scale.item())
+        nval = val.steps if val is not None else 0
+        ts_all, vs_all = self._stat_buffers(train.steps, nval)    # pinned once (cudaHostAlloc is slow)
         for ep in range(epochs):
             self.model.train()
-            ts = torch.zeros(train.steps, 2, dtype=torch.float32)
-            ts = ts.pin_memory() if pinned else ts
+            ts = ts_all[: train.steps]
             for i, (x, y) in enumerate(train.epoch()):
                 out = self.train_step(x, y)
                 ts[i].copy_(out, non_blocking=True)       # D2H of the step's loss/accuracy
             vs = None
             if val is not None and val.steps > 0:
                 self.model.eval()
-                vs = torch.zeros(val.steps, 2, dtype=torch.float32)
-                vs = vs.pin_memory() if pinned else vs
+                vs = vs_all[:nval]
                 for i, (x, y) in enumerate(val.epoch()):
                     out = self.eval_step(x, y)
                     vs[i].copy_(out, non_blocking=True)
@@ -199,7 +199,7 @@ class LocalTrainer:
             acc = float(ts[:, 1].sum()) / (train.steps * B)
             vloss = float(vs[:, 0].mean()) if vs is not None else float("nan")
             vacc = float(vs[:, 1].sum()) / (val.steps * B) if vs is not None else float("nan")
-            st = EpochStats(loss, acc, vloss, vacc, float(self.lr_scale.item()))
+            st = EpochStats(loss, acc, vloss, vacc, lr_scale_host)
             hist.append(st)
             if on_epoch:
                 on_epoch(ep, st)
@@ -216,9 +216,10 @@ class LocalTrainer:
                 wait_es += 1
                 wait_lr += 1
                 if reduce_lr_patience is not None and wait_lr >= reduce_lr_patience:
-                    cur = float(self.lr_scale.item()) * self.cfg.lr
+                    cur = lr_scale_host * self.cfg.lr
                     new = max(cur * reduce_lr_factor, min_lr)
-                    self.lr_scale.fill_(new / self.cfg.lr)
+                    lr_scale_host = new / self.cfg.lr
+                    self.lr_scale.fill_(lr_scale_host)
                     wait_lr = 0
                 if early_stopping is not None and wait_es >= early_stopping:
                     if restore_best and best_weights is not None:
@@ -227,6 +228,14 @@ class LocalTrainer:
                             self.engine.after_restore()
                     break
         return hist
+
+    def _stat_buffers(self, ntrain: int, nval: int):
+        cur = getattr(self, "_stats", None)
+        if cur is None or cur[0].shape[0] < ntrain or cur[1].shape[0] < max(nval, 1):
+            mk = (lambda n: torch.zeros(n, 2, dtype=torch.float32).pin_memory()) if self.cuda else \
+                (lambda n: torch.zeros(n, 2, dtype=torch.float32))
+            self._stats = (mk(max(ntrain, 1)), mk(max(nval, 1)))
+        return self._stats
 
     def reset_optimizer(self) -> None:
         self.m.zero_(); self.v.zero_(); self.step_t.zero_(); self.lr_scale.fill_(1.0)

@@ -92,19 +92,24 @@ class FusedTransport(Transport):
     def allreduce(self, data: torch.Tensor) -> torch.Tensor:
         numel = data.numel()
         base = self.sym.tensor
-        if data.data_ptr() != base.data_ptr():
+        off = data.data_ptr() - base.data_ptr()
+        inside = 0 <= off and off + numel * 8 <= self.max_numel * 8 and off % 16 == 0
+        if not inside:
             # caller did not encrypt in place: stage into the symmetric buffer
             self.buffer(numel).copy_(data.reshape(-1))
+            off = 0
         algo = self.pick_algo(numel * 8)
         self.last_algo = algo
         blocks = self.pick_blocks(numel, algo)
-        self.ops.allreduce_modq(self.sym.ptrs, self.sig.ptrs, self.sym.mc_ptr,
-                                self.out if algo == "one_shot" else None, self.status,
+        e0 = off // 8                              # a view of the symmetric buffer (chunked pipelines)
+        out = self.out[e0:e0 + numel] if algo == "one_shot" else None
+        self.ops.allreduce_modq([p + off for p in self.sym.ptrs], self.sig.ptrs,
+                                self.sym.mc_ptr + off if self.sym.mc_ptr else 0, out, self.status,
                                 self.ctx.consts_cpu, numel, data.shape[-2], self.ctx.logn,
                                 self.rank, self.world, ALGOS[algo], blocks, self.threads,
                                 self.timeout_ms)
         src = self.out if algo == "one_shot" else base
-        return src[:numel].view(data.shape)
+        return src[e0:e0 + numel].view(data.shape)
 
     def check_status(self) -> None:
         """Raises if a bounded spin-wait timed out in a previous launch (failure detection)."""

@@ -171,3 +171,22 @@ def test_fused_allreduce_timeout_is_detected():
                        status, g.consts_cpu, numel, 1, 12, 0, 2, 0, 2, 64, 50)
     torch.cuda.synchronize()
     assert int(status.item()) != 0
+
+
+def test_pipelined_fedavg_matches_unchunked():
+    """Chunked 3-stream encrypt / all-reduce / decrypt pipeline == the single-shot path."""
+    from hefl_b200.config import FLConfig
+    from hefl_b200.fl import FederatedRunner
+
+    cfg = FLConfig(model="medcnn", local_epochs=1, steps_per_epoch=1, val_steps=0, nn_backend="cudnn",
+                   transport="fused", device="cuda")
+    run = FederatedRunner(cfg, device=torch.device("cuda"))
+    w = run.pack.flat.clone()
+    run.fedavg_pipelined(chunk_cts=20)
+    torch.cuda.synchronize()
+    assert (run.pack.flat - w).abs().max() < 1e-6        # one client: average == its own weights
+    run.pack.load_flat(w)
+    ct = run.encrypt_update()
+    agg = run.aggregate(ct)
+    run.decrypt_apply(agg)
+    assert (run.pack.flat - w).abs().max() < 1e-6

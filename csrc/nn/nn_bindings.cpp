@@ -149,7 +149,8 @@ void head_forward_backward(const Tensor& feat, const Tensor& flat, Tensor grad, 
   TORCH_CHECK(feat.numel() == B * F && dfeat.numel() == B * F, "feat/dfeat must be [B,F]");
   TORCH_CHECK(flat.is_cuda() && flat.scalar_type() == at::kFloat && grad.scalar_type() == at::kFloat, "float32 parameter buffers required");
   TORCH_CHECK(y.is_cuda() && y.scalar_type() == at::kLong && y.numel() == B, "labels must be int64 [B]");
-  TORCH_CHECK(h1_buf.numel() >= B * H1 && dh1_buf.numel() >= B * H1 && out.numel() >= 2, "scratch too small");
+  TORCH_CHECK(h1_buf.numel() >= B * H1 && dh1_buf.numel() >= B * (H1 + H2) && out.numel() >= 2, "scratch too small");
+  TORCH_CHECK(B % 2 == 0 && H2 % 4 == 0 && H1 % 4 == 0 && F % 8 == 0, "head dims must be even / multiples of 4 / 8");
   const float* p = flat.data_ptr<float>();
   float* g = grad.data_ptr<float>();
   hefl::nn::head_forward_backward(feat.data_ptr(), p + offs[0], p + offs[1], p + offs[2], p + offs[3], p + offs[4],

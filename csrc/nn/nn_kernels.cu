@@ -249,56 +249,57 @@ void conv_grad_finalize(float* dW32, const ConvLayerTable& t, float* grad, cudaS
 
 // ------------------------------------------------------------------------------------------
 // Dense head of the sequential CNNs: Flatten -> Dense(H1, ReLU) -> Dense(H2, ReLU) -> Dense(C)
-// -> softmax cross-entropy (FLPyfhelin.py:133-136, :141), forward AND backward in three launches
-// (K16/K17). The head is ~13 MFLOP at batch 32: latency-, not throughput-bound, so plain fp32
-// CUDA-core kernels with shared-memory staging beat a chain of ~30 library kernels.
+// -> softmax cross-entropy (FLPyfhelin.py:133-136, :141), forward AND backward in four launches
+// (K16/K17). ~13 MFLOP at batch 32: latency- and shared-memory-bound, so the work is spread over
+// many CTAs per phase, operands are staged with all loads in flight, and every thread reuses
+// each shared-memory operand for several FMAs.
+//   k1  h1 = relu(feat W1^T + b1)                                  grid H1/4
+//   k2  h2, logits, loss, dlogits, dW3, db3, dh2                   1 CTA (0.3 MFLOP)
+//   k3  dW2, db2, dh1 (column slices of 16)                        grid H1/16
+//   k4  dW1, db1, dfeat (column slices of 16)                      grid F/16
 // ------------------------------------------------------------------------------------------
 namespace hefl {
 namespace nn {
 
-// h1[b][j] = relu(b1[j] + sum_k feat[b][k] * W1[j][k]). One CTA = 8 neurons; thread = (sample, neuron);
-// both operands are staged in shared memory (coalesced loads), 4 independent accumulators per thread.
-__global__ void __launch_bounds__(256)
+// k1: one CTA = 4 neurons; thread = (sample b, neuron jj); feat and the 4 weight rows in smem.
+__global__ void __launch_bounds__(128)
 head_fc1_fwd_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict__ W1,
                     const float* __restrict__ b1, float* __restrict__ h1, int B, int F, int H1) {
   extern __shared__ float sm1[];
   const int FP = F + 1;
   float* fs = sm1;                 // [B][F+1]
-  float* ws = fs + B * FP;         // [8][F+1]
-  const int j0 = blockIdx.x * 8;
-  // staged with 16-byte loads, several in flight per thread (the loads, not the FMAs, set the latency)
+  float* ws = fs + B * FP;         // [4][F+1]
+  const int j0 = blockIdx.x * 4;
   const int F8 = F >> 3, F4 = F >> 2;
-  for (int b = 0; b < B; ++b) {
-    const uint4* src = reinterpret_cast<const uint4*>(feat + (size_t)b * F);
-#pragma unroll 2
-    for (int k8 = threadIdx.x; k8 < F8; k8 += blockDim.x) {
-      const uint4 v = src[k8];
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-      float* dst = fs + b * FP + k8 * 8;
+  const uint4* src = reinterpret_cast<const uint4*>(feat);
+#pragma unroll 8
+  for (int i = threadIdx.x; i < B * F8; i += blockDim.x) {   // B*F/8 16-byte loads, 8+ in flight per thread
+    const uint4 v = src[i];
+    const int b = i / F8, k8 = i - b * F8;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float* dst = fs + b * FP + k8 * 8;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        dst[2 * q] = __uint_as_float(w[q] << 16);
-        dst[2 * q + 1] = __uint_as_float(w[q] & 0xFFFF0000u);
-      }
+    for (int q = 0; q < 4; ++q) {
+      dst[2 * q] = __uint_as_float(w[q] << 16);
+      dst[2 * q + 1] = __uint_as_float(w[q] & 0xFFFF0000u);
     }
   }
-#pragma unroll
-  for (int jj = 0; jj < 8; ++jj) {
-    const bool ok = (j0 + jj) < H1;
-    const float4* src = reinterpret_cast<const float4*>(W1 + (size_t)(ok ? j0 + jj : 0) * F);
-    for (int k4 = threadIdx.x; k4 < F4; k4 += blockDim.x) {
-      const float4 v = ok ? src[k4] : make_float4(0.f, 0.f, 0.f, 0.f);
-      float* dst = ws + jj * FP + k4 * 4;
-      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
-    }
+#pragma unroll 4
+  for (int i = threadIdx.x; i < 4 * F4; i += blockDim.x) {
+    const int jj = i / F4, k4 = i - jj * F4;
+    const float4 v = (j0 + jj) < H1 ? reinterpret_cast<const float4*>(W1 + (size_t)(j0 + jj) * F)[k4]
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    float* dst = ws + jj * FP + k4 * 4;
+    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
   }
   __syncthreads();
-  const int b = threadIdx.x >> 3, jj = threadIdx.x & 7;
+  const int b = threadIdx.x >> 2, jj = threadIdx.x & 3;
   if (b < B && j0 + jj < H1) {
     const float* fr = fs + b * FP;
     const float* wr = ws + jj * FP;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     int k = 0;
+#pragma unroll 4
     for (; k + 4 <= F; k += 4) {
       a0 = fmaf(fr[k], wr[k], a0);
       a1 = fmaf(fr[k + 1], wr[k + 1], a1);
@@ -315,91 +316,99 @@ struct HeadMidArgs {
   const float* h1;      // [B][H1]
   const float *W2, *b2, *W3, *b3;
   const int64_t* y;     // [B]
-  float *gW2, *gb2, *gW3, *gb3;
-  float* dh1;           // [B][H1] out
+  float *gW3, *gb3;
+  float* dh2;           // [B][H2] out
   float* out;           // [2]: loss, ncorrect
   int B, H1, H2, C, train;
 };
 
-__global__ void __launch_bounds__(1024)
+// k2: fc2 (each thread: 2 samples x 4 neurons, operands reused from registers), fc3, loss, dW3, dh2.
+__global__ void __launch_bounds__(256)
 head_mid_kernel(const HeadMidArgs a) {
   extern __shared__ float sm[];
   const int B = a.B, H1 = a.H1, H2 = a.H2, C = a.C;
   float* h1 = sm;                       // [B][H1+1]
   float* W2 = h1 + B * (H1 + 1);        // [H2][H1+1]
   float* h2 = W2 + H2 * (H1 + 1);       // [B][H2+1]
-  float* dh2 = h2 + B * (H2 + 1);       // [B][H2+1]
-  float* lg = dh2 + B * (H2 + 1);       // [B][C]  logits -> dlogits
+  float* lg = h2 + B * (H2 + 1);        // [B][C]  logits -> dlogits
   float* red = lg + B * C;              // [2*B]
   float* W3 = red + 2 * B;              // [C][H2]
-  float* b2s = W3 + C * H2;             // [H2]
-  float* b3s = b2s + H2;                // [C]
   const int tid = threadIdx.x, nt = blockDim.x;
-  {
-    const int H14 = H1 >> 2;
-    const float4* s1 = reinterpret_cast<const float4*>(a.h1);
-    const float4* s2 = reinterpret_cast<const float4*>(a.W2);
+  const int H14 = H1 >> 2;
 #pragma unroll 4
-    for (int i = tid; i < B * H14; i += nt) {
-      const float4 v = s1[i];
-      float* d = h1 + (i / H14) * (H1 + 1) + (i % H14) * 4;
-      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-    }
-#pragma unroll 4
-    for (int i = tid; i < H2 * H14; i += nt) {
-      const float4 v = s2[i];
-      float* d = W2 + (i / H14) * (H1 + 1) + (i % H14) * 4;
-      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-    }
-    for (int i = tid; i < C * H2; i += nt) W3[i] = a.W3[i];
-    for (int i = tid; i < H2; i += nt) b2s[i] = a.b2[i];
-    for (int i = tid; i < C; i += nt) b3s[i] = a.b3[i];
+  for (int i = tid; i < B * H14; i += nt) {
+    const float4 v = reinterpret_cast<const float4*>(a.h1)[i];
+    float* d = h1 + (i / H14) * (H1 + 1) + (i % H14) * 4;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
   }
+#pragma unroll 8
+  for (int i = tid; i < H2 * H14; i += nt) {
+    const float4 v = reinterpret_cast<const float4*>(a.W2)[i];
+    float* d = W2 + (i / H14) * (H1 + 1) + (i % H14) * 4;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  for (int i = tid; i < C * H2; i += nt) W3[i] = a.W3[i];
   __syncthreads();
-  for (int o = tid; o < B * H2; o += nt) {                     // fc2
-    const int b = o / H2, j = o % H2;
-    float a0 = b2s[j], a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    const float* hr = h1 + b * (H1 + 1);
-    const float* wr = W2 + j * (H1 + 1);
-    int i = 0;
-    for (; i + 4 <= H1; i += 4) {
-      a0 = fmaf(hr[i], wr[i], a0); a1 = fmaf(hr[i + 1], wr[i + 1], a1);
-      a2 = fmaf(hr[i + 2], wr[i + 2], a2); a3 = fmaf(hr[i + 3], wr[i + 3], a3);
+  {  // fc2: tiles of 2 samples x 4 neurons
+    const int tiles_j = H2 >> 2, tiles = (B >> 1) * tiles_j;
+    for (int t = tid; t < tiles; t += nt) {
+      const int b0 = (t / tiles_j) * 2, j0 = (t % tiles_j) * 4;
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      for (int i = 0; i < H1; ++i) {
+        const float x0 = h1[b0 * (H1 + 1) + i], x1 = h1[(b0 + 1) * (H1 + 1) + i];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float w = W2[(j0 + q) * (H1 + 1) + i];
+          acc[0][q] = fmaf(x0, w, acc[0][q]);
+          acc[1][q] = fmaf(x1, w, acc[1][q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float bb = a.b2[j0 + q];
+        const float y0 = acc[0][q] + bb, y1 = acc[1][q] + bb;
+        h2[b0 * (H2 + 1) + j0 + q] = y0 > 0.f ? y0 : 0.f;
+        h2[(b0 + 1) * (H2 + 1) + j0 + q] = y1 > 0.f ? y1 : 0.f;
+      }
     }
-    for (; i < H1; ++i) a0 = fmaf(hr[i], wr[i], a0);
-    const float acc = (a0 + a1) + (a2 + a3);
-    h2[b * (H2 + 1) + j] = acc > 0.f ? acc : 0.f;
   }
   __syncthreads();
   for (int o = tid; o < B * C; o += nt) {                      // fc3
     const int b = o / C, c = o % C;
-    float acc = b3s[c];
-    for (int j = 0; j < H2; ++j) acc = fmaf(h2[b * (H2 + 1) + j], W3[c * H2 + j], acc);
-    lg[o] = acc;
-  }
-  __syncthreads();
-  if (tid < B) {                                               // softmax cross-entropy per sample
-    float mx = -1e30f;
-    int am = 0;
-    for (int c = 0; c < C; ++c) if (lg[tid * C + c] > mx) { mx = lg[tid * C + c]; am = c; }
-    float s = 0.f;
-    for (int c = 0; c < C; ++c) s += __expf(lg[tid * C + c] - mx);
-    const int yy = (int)a.y[tid];
-    red[tid] = -(lg[tid * C + yy] - mx - __logf(s));
-    red[B + tid] = am == yy ? 1.f : 0.f;
-    const float invB = 1.f / B;
-    for (int c = 0; c < C; ++c) {
-      const float p = __expf(lg[tid * C + c] - mx) / s;
-      lg[tid * C + c] = (p - (c == yy ? 1.f : 0.f)) * invB;   // dlogits
+    float a0 = a.b3[c], a1 = 0.f;
+    int j = 0;
+    for (; j + 2 <= H2; j += 2) {
+      a0 = fmaf(h2[b * (H2 + 1) + j], W3[c * H2 + j], a0);
+      a1 = fmaf(h2[b * (H2 + 1) + j + 1], W3[c * H2 + j + 1], a1);
     }
+    for (; j < H2; ++j) a0 = fmaf(h2[b * (H2 + 1) + j], W3[c * H2 + j], a0);
+    lg[o] = a0 + a1;
   }
   __syncthreads();
-  if (tid == 0) {
+  if (tid < 32) {                                              // warp 0: softmax cross-entropy, one lane per sample
     float l = 0.f, nc = 0.f;
-    for (int b = 0; b < B; ++b) { l += red[b]; nc += red[B + b]; }
-    a.out[0] = l / B;
-    a.out[1] = nc;
+    if (tid < B) {
+      float mx = -1e30f;
+      int am = 0;
+      for (int c = 0; c < C; ++c) if (lg[tid * C + c] > mx) { mx = lg[tid * C + c]; am = c; }
+      float s = 0.f;
+      for (int c = 0; c < C; ++c) s += __expf(lg[tid * C + c] - mx);
+      const int yy = (int)a.y[tid];
+      l = -(lg[tid * C + yy] - mx - __logf(s));
+      nc = am == yy ? 1.f : 0.f;
+      const float invB = 1.f / B;
+      for (int c = 0; c < C; ++c) {
+        const float p = __expf(lg[tid * C + c] - mx) / s;
+        lg[tid * C + c] = (p - (c == yy ? 1.f : 0.f)) * invB;   // dlogits
+      }
+    }
+    for (int off = 16; off; off >>= 1) {                       // all 32 lanes take part (B <= 32)
+      l += __shfl_xor_sync(0xffffffffu, l, off);
+      nc += __shfl_xor_sync(0xffffffffu, nc, off);
+    }
+    if (tid == 0) { a.out[0] = l / B; a.out[1] = nc; }
   }
+  __syncthreads();
   if (!a.train) return;
   for (int o = tid; o < C * H2 + C; o += nt) {                 // dW3, db3
     if (o < C * H2) {
@@ -414,45 +423,63 @@ head_mid_kernel(const HeadMidArgs a) {
       a.gb3[c] = acc;
     }
   }
-  for (int o = tid; o < B * H2; o += nt) {                     // dh2
+  for (int o = tid; o < B * H2; o += nt) {                     // dh2 -> global for k3
     const int b = o / H2, j = o % H2;
     float acc = 0.f;
     for (int c = 0; c < C; ++c) acc = fmaf(lg[b * C + c], W3[c * H2 + j], acc);
-    dh2[b * (H2 + 1) + j] = h2[b * (H2 + 1) + j] > 0.f ? acc : 0.f;
-  }
-  __syncthreads();
-  for (int o = tid; o < H2 * H1 + H2; o += nt) {               // dW2, db2
-    if (o < H2 * H1) {
-      const int j = o / H1, i = o % H1;
-      float a0 = 0.f, a1 = 0.f;
-      int b = 0;
-      for (; b + 2 <= B; b += 2) {
-        a0 = fmaf(dh2[b * (H2 + 1) + j], h1[b * (H1 + 1) + i], a0);
-        a1 = fmaf(dh2[(b + 1) * (H2 + 1) + j], h1[(b + 1) * (H1 + 1) + i], a1);
-      }
-      for (; b < B; ++b) a0 = fmaf(dh2[b * (H2 + 1) + j], h1[b * (H1 + 1) + i], a0);
-      a.gW2[o] = a0 + a1;
-    } else {
-      const int j = o - H2 * H1;
-      float acc = 0.f;
-      for (int b = 0; b < B; ++b) acc += dh2[b * (H2 + 1) + j];
-      a.gb2[j] = acc;
-    }
-  }
-  for (int o = tid; o < B * H1; o += nt) {                     // dh1
-    const int b = o / H1, i = o % H1;
-    float a0 = 0.f, a1 = 0.f;
-    int j = 0;
-    for (; j + 2 <= H2; j += 2) {
-      a0 = fmaf(dh2[b * (H2 + 1) + j], W2[j * (H1 + 1) + i], a0);
-      a1 = fmaf(dh2[b * (H2 + 1) + j + 1], W2[(j + 1) * (H1 + 1) + i], a1);
-    }
-    for (; j < H2; ++j) a0 = fmaf(dh2[b * (H2 + 1) + j], W2[j * (H1 + 1) + i], a0);
-    a.dh1[o] = h1[b * (H1 + 1) + i] > 0.f ? (a0 + a1) : 0.f;
+    a.dh2[o] = h2[b * (H2 + 1) + j] > 0.f ? acc : 0.f;
   }
 }
 
-// dW1[j][k] = sum_b dh1[b][j] feat[b][k]; db1[j] = sum_b dh1[b][j]; dfeat[b][k] = sum_j dh1[b][j] W1[j][k].
+// k3: one CTA owns 16 columns i of layer 2's input: dW2[:, i], dh1[:, i]; CTA 0 also db2.
+__global__ void __launch_bounds__(256)
+head_fc2_bwd_kernel(const float* __restrict__ dh2g, const float* __restrict__ h1g, const float* __restrict__ W2,
+                    float* __restrict__ gW2, float* __restrict__ gb2, float* __restrict__ dh1, int B, int H1, int H2) {
+  extern __shared__ float sm[];
+  float* d = sm;                       // [B][H2+1]
+  float* hs = d + B * (H2 + 1);        // [B][16]
+  float* ws = hs + B * 16;             // [H2][17]
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int i0 = blockIdx.x * 16;
+#pragma unroll 4
+  for (int i = tid; i < B * H2; i += nt) d[(i / H2) * (H2 + 1) + i % H2] = dh2g[i];
+#pragma unroll 2
+  for (int i = tid; i < B * 16; i += nt) hs[i] = (i0 + (i & 15)) < H1 ? h1g[(i >> 4) * H1 + i0 + (i & 15)] : 0.f;
+#pragma unroll 4
+  for (int i = tid; i < H2 * 16; i += nt) ws[(i >> 4) * 17 + (i & 15)] = (i0 + (i & 15)) < H1 ? W2[(size_t)(i >> 4) * H1 + i0 + (i & 15)] : 0.f;
+  __syncthreads();
+  for (int o = tid; o < H2 * 16; o += nt) {                    // dW2[j][i0+k]
+    const int j = o >> 4, k = o & 15;
+    float a0 = 0.f, a1 = 0.f;
+    int b = 0;
+    for (; b + 2 <= B; b += 2) {
+      a0 = fmaf(d[b * (H2 + 1) + j], hs[b * 16 + k], a0);
+      a1 = fmaf(d[(b + 1) * (H2 + 1) + j], hs[(b + 1) * 16 + k], a1);
+    }
+    for (; b < B; ++b) a0 = fmaf(d[b * (H2 + 1) + j], hs[b * 16 + k], a0);
+    if (i0 + k < H1) gW2[(size_t)j * H1 + i0 + k] = a0 + a1;
+  }
+  for (int o = tid; o < B * 16; o += nt) {                     // dh1[b][i0+k]
+    const int b = o >> 4, k = o & 15;
+    float a0 = 0.f, a1 = 0.f;
+    int j = 0;
+    for (; j + 2 <= H2; j += 2) {
+      a0 = fmaf(d[b * (H2 + 1) + j], ws[j * 17 + k], a0);
+      a1 = fmaf(d[b * (H2 + 1) + j + 1], ws[(j + 1) * 17 + k], a1);
+    }
+    for (; j < H2; ++j) a0 = fmaf(d[b * (H2 + 1) + j], ws[j * 17 + k], a0);
+    if (i0 + k < H1) dh1[b * H1 + i0 + k] = hs[b * 16 + k] > 0.f ? (a0 + a1) : 0.f;
+  }
+  if (blockIdx.x == 0) {
+    for (int j = tid; j < H2; j += nt) {
+      float acc = 0.f;
+      for (int b = 0; b < B; ++b) acc += d[b * (H2 + 1) + j];
+      gb2[j] = acc;
+    }
+  }
+}
+
+// k4: dW1[j][k] = sum_b dh1[b][j] feat[b][k]; db1[j] = sum_b dh1[b][j]; dfeat[b][k] = sum_j dh1[b][j] W1[j][k].
 // One CTA owns 16 input columns k.
 __global__ void __launch_bounds__(256)
 head_fc1_bwd_kernel(const float* __restrict__ dh1, const __nv_bfloat16* __restrict__ feat,
@@ -464,13 +491,14 @@ head_fc1_bwd_kernel(const float* __restrict__ dh1, const __nv_bfloat16* __restri
   float* ws = fs + B * 16;             // [H1][17]
   const int tid = threadIdx.x, nt = blockDim.x;
   const int k0 = blockIdx.x * 16;
-#pragma unroll 4
+#pragma unroll 8
   for (int i = tid; i < B * H1; i += nt) d[(i / H1) * (H1 + 1) + i % H1] = dh1[i];
+#pragma unroll 2
   for (int i = tid; i < B * 16; i += nt) {
     const int b = i >> 4, k = i & 15;
     fs[i] = k0 + k < F ? __bfloat162float(feat[b * F + k0 + k]) : 0.f;
   }
-#pragma unroll 4
+#pragma unroll 8
   for (int i = tid; i < H1 * 16; i += nt) {
     const int j = i >> 4, k = i & 15;
     ws[j * 17 + k] = k0 + k < F ? W1[(size_t)j * F + k0 + k] : 0.f;
@@ -478,15 +506,25 @@ head_fc1_bwd_kernel(const float* __restrict__ dh1, const __nv_bfloat16* __restri
   __syncthreads();
   for (int o = tid; o < H1 * 16; o += nt) {
     const int j = o >> 4, k = o & 15;
-    float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc = fmaf(d[b * (H1 + 1) + j], fs[b * 16 + k], acc);
-    if (k0 + k < F) gW1[(size_t)j * F + k0 + k] = acc;
+    float a0 = 0.f, a1 = 0.f;
+    int b = 0;
+    for (; b + 2 <= B; b += 2) {
+      a0 = fmaf(d[b * (H1 + 1) + j], fs[b * 16 + k], a0);
+      a1 = fmaf(d[(b + 1) * (H1 + 1) + j], fs[(b + 1) * 16 + k], a1);
+    }
+    for (; b < B; ++b) a0 = fmaf(d[b * (H1 + 1) + j], fs[b * 16 + k], a0);
+    if (k0 + k < F) gW1[(size_t)j * F + k0 + k] = a0 + a1;
   }
   for (int o = tid; o < B * 16; o += nt) {
     const int b = o >> 4, k = o & 15;
-    float acc = 0.f;
-    for (int j = 0; j < H1; ++j) acc = fmaf(d[b * (H1 + 1) + j], ws[j * 17 + k], acc);
-    if (k0 + k < F) dfeat[b * F + k0 + k] = __float2bfloat16(acc);
+    float a0 = 0.f, a1 = 0.f;
+    int j = 0;
+    for (; j + 2 <= H1; j += 2) {
+      a0 = fmaf(d[b * (H1 + 1) + j], ws[j * 17 + k], a0);
+      a1 = fmaf(d[b * (H1 + 1) + j + 1], ws[(j + 1) * 17 + k], a1);
+    }
+    for (; j < H1; ++j) a0 = fmaf(d[b * (H1 + 1) + j], ws[j * 17 + k], a0);
+    if (k0 + k < F) dfeat[b * F + k0 + k] = __float2bfloat16(a0 + a1);
   }
   if (blockIdx.x == 0) {
     for (int j = tid; j < H1; j += nt) {
@@ -502,20 +540,23 @@ void head_forward_backward(const void* feat, const float* W1, const float* b1, c
                            float* gb2, float* gW3, float* gb3, void* dfeat, float* h1_buf, float* dh1_buf,
                            float* out, int B, int F, int H1, int H2, int C, int train, cudaStream_t st) {
   const auto* f = reinterpret_cast<const __nv_bfloat16*>(feat);
-  const int smem_a = (B + 8) * (F + 1) * 4;
+  float* dh2_buf = dh1_buf + (size_t)B * H1;                  // scratch tail: [B][H2]
+  const int smem_a = (B + 4) * (F + 1) * 4;
   cudaFuncSetAttribute(head_fc1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
-  head_fc1_fwd_kernel<<<(H1 + 7) / 8, 256, smem_a, st>>>(f, W1, b1, h1_buf, B, F, H1);
-  HeadMidArgs a{h1_buf, W2, b2, W3, b3, y, gW2, gb2, gW3, gb3, dh1_buf, out, B, H1, H2, C, train};
-  const int smem_b = (B * (H1 + 1) + H2 * (H1 + 1) + 2 * B * (H2 + 1) + B * C + 2 * B + C * H2 + H2 + C) * 4;
+  head_fc1_fwd_kernel<<<(H1 + 3) / 4, 128, smem_a, st>>>(f, W1, b1, h1_buf, B, F, H1);
+  HeadMidArgs a{h1_buf, W2, b2, W3, b3, y, gW3, gb3, dh2_buf, out, B, H1, H2, C, train};
+  const int smem_b = (B * (H1 + 1) + H2 * (H1 + 1) + B * (H2 + 1) + B * C + 2 * B + C * H2) * 4;
   cudaFuncSetAttribute(head_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
-  head_mid_kernel<<<1, 1024, smem_b, st>>>(a);
+  head_mid_kernel<<<1, 256, smem_b, st>>>(a);
   hefl::cuda::note_launch(2);
   if (train) {
-    const int smem_c = (B * (H1 + 1) + B * 16 + H1 * 17) * 4;
-    cudaFuncSetAttribute(head_fc1_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c);
-    head_fc1_bwd_kernel<<<(F + 15) / 16, 256, smem_c, st>>>(dh1_buf, f, W1, gW1, gb1,
+    const int smem_c = (B * (H2 + 1) + B * 16 + H2 * 17) * 4;
+    head_fc2_bwd_kernel<<<(H1 + 15) / 16, 256, smem_c, st>>>(dh2_buf, h1_buf, W2, gW2, gb2, dh1_buf, B, H1, H2);
+    const int smem_d = (B * (H1 + 1) + B * 16 + H1 * 17) * 4;
+    cudaFuncSetAttribute(head_fc1_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_d);
+    head_fc1_bwd_kernel<<<(F + 15) / 16, 256, smem_d, st>>>(dh1_buf, f, W1, gW1, gb1,
                                                             reinterpret_cast<__nv_bfloat16*>(dfeat), B, F, H1);
-    hefl::cuda::note_launch();
+    hefl::cuda::note_launch(2);
   }
 }
 

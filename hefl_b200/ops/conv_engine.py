@@ -94,7 +94,7 @@ class MedCNNEngine:
         self.bias = [pack.flat[self.b_off[l]: self.b_off[l] + self.Co[l]] for l in range(self.n)]
         # dense head: fused kernels when it is the reference's 3-layer shape, else PyTorch autograd
         fcs = list(model.fcs)
-        self.fused_head = len(fcs) == 3 and B <= 32
+        self.fused_head = len(fcs) == 3 and B <= 32 and B % 2 == 0
         if self.fused_head:
             nfc = self.n * 2 + 1
             self.head_offs = []
@@ -102,7 +102,7 @@ class MedCNNEngine:
                 self.head_offs += [offs[f"c_{nfc + i}_0"], offs[f"c_{nfc + i}_1"]]
             self.F, self.H1, self.H2, self.C = fcs[0].in_features, fcs[0].out_features, fcs[1].out_features, fcs[2].out_features
             self.h1_buf = torch.zeros(B * self.H1, dtype=torch.float32, device=device)
-            self.dh1_buf = torch.zeros(B * self.H1, dtype=torch.float32, device=device)
+            self.dh1_buf = torch.zeros(B * (self.H1 + self.H2), dtype=torch.float32, device=device)
             self.dfeat = torch.zeros(B, self.F, **bf)
         self.theta = torch.zeros(B, 2, 3, dtype=torch.float32, device=device)
         self.aug_seed = (cfg.seed * 2654435761 + 12345) & 0x7FFFFFFFFFFFFFFF or 1

@@ -134,13 +134,15 @@ struct TapGemmCfg {
   static constexpr int BAR_BYTES = 384;
   static constexpr int BUDGET = 225 * 1024;
   static constexpr int NBUF_RAW = (BUDGET - W_BYTES - BAR_BYTES - 1024) / HALO;
-  static constexpr int NBUF = NBUF_RAW > 8 ? 8 : NBUF_RAW;   // bytes in flight bound the small-channel layers
+  // ring depth beyond 3 and more than 2 TMEM tile buffers measured no gain; small footprints let a
+  // wgrad CTA and a dgrad/forward CTA share an SM (the backward pass runs them on two streams)
+  static constexpr int NBUF = NBUF_RAW > 3 ? 3 : NBUF_RAW;
   static constexpr int SMEM = W_BYTES + NBUF * HALO + BAR_BYTES + 1024;
   // TMEM tile buffers: the MMA -> epilogue -> MMA hand-off costs ~1500 cycles of mbarrier latency
   // (measured with all work disabled: 750 cycles/tile with 2 buffers), so small-channel layers use
   // up to 8 buffers to keep several tiles in flight.
   static constexpr int NT_RAW = 512 / (NACC * CO);
-  static constexpr int NT = NT_RAW > 8 ? 8 : NT_RAW;
+  static constexpr int NT = NT_RAW > 2 ? 2 : NT_RAW;
   static constexpr int ACC_COLS = NT * NACC * CO;
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
   static_assert(NT >= 2, "need at least two TMEM tile buffers");
@@ -470,7 +472,7 @@ struct WgradCfg {
   // deep ring: stages are small (one X row segment + one dY chunk), so the number of bytes in
   // flight, not the MMA rate, bounds throughput (measured: 6 stages -> 204 us on layer 1)
   static constexpr int NSTAGE_RAW = (200 * 1024 - ONES_BYTES) / STAGE_FULL;
-  static constexpr int NSTAGE = NSTAGE_RAW > 28 ? 28 : NSTAGE_RAW;
+  static constexpr int NSTAGE = NSTAGE_RAW > 8 ? 8 : NSTAGE_RAW;
   static constexpr int SMEM = NSTAGE * STAGE_FULL + ONES_BYTES + 512 + 1024;
   static constexpr int COLS = (NACC + 1) * COT;                // + bias accumulator
   static_assert(NSTAGE >= 4, "ring needs 3 live stages + 1 in flight");

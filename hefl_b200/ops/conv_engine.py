@@ -106,6 +106,9 @@ class MedCNNEngine:
             self.dfeat = torch.zeros(B, self.F, **bf)
         self.theta = torch.zeros(B, 2, 3, dtype=torch.float32, device=device)
         self.aug_seed = (cfg.seed * 2654435761 + 12345) & 0x7FFFFFFFFFFFFFFF or 1
+        # weight gradients run on a side stream, concurrently with the dgrad / un-pool chain
+        self.side = torch.cuda.Stream(device)
+        self.two_streams = True
         self.step_ref: Optional[torch.Tensor] = None     # device step counter (set by the trainer)
         self.after_restore()
 
@@ -174,13 +177,22 @@ class MedCNNEngine:
             out[0] = loss.detach()
             out[1] = (logits.argmax(1) == y).sum()
             g = feat.grad.to(torch.bfloat16).view_as(feat_bf).contiguous()
+        main = torch.cuda.current_stream(self.device)
         for l in range(self.n - 1, -1, -1):
             h = self.H[l]
             self.ops.unpool_relu(g, self.amax[l], self.X[l + 1], self.dY[l], self.B, h, h, self.Co[l])
-            self.ops.conv_wgrad(self.X[l], self.dY[l], self._dw(l), self.B, h, h, self.CK[l], self.Co[l])
+            if self.two_streams and l > 0:
+                # wgrad(l) only needs X[l] and dY[l]; dgrad(l) -> unpool(l-1) -> ... proceeds meanwhile
+                self.side.wait_stream(main)
+                with torch.cuda.stream(self.side):
+                    self.ops.conv_wgrad(self.X[l], self.dY[l], self._dw(l), self.B, h, h, self.CK[l], self.Co[l])
+            else:
+                self.ops.conv_wgrad(self.X[l], self.dY[l], self._dw(l), self.B, h, h, self.CK[l], self.Co[l])
             if l > 0:
                 self.ops.conv_dgrad(self.dY[l], self._wd(l), self.gX[l], self.B, h, h, self.Co[l], self.Ci[l])
                 g = self.gX[l]
+        if self.two_streams:
+            main.wait_stream(self.side)
         self.ops.conv_grad_finalize(self.dW32, self.table, self.pack.grad)
 
     def eval_step(self, x_u8: torch.Tensor, y: torch.Tensor, out: torch.Tensor) -> None:

@@ -62,18 +62,23 @@ def main():
         loss.backward()
         return feat.grad.to(torch.bfloat16)
     res["head(torch fwd+bwd)"] = timeit(head)
-    res["head(fused kernels)"] = timeit(lambda: ops.head_forward_backward(eng.X[eng.n], pack.flat, pack.grad, eng.head_offs, y, eng.dfeat, eng.h1_buf, eng.dh1_buf, out, B, eng.F, eng.H1, eng.H2, eng.C, True))
+    res["head(fused kernels)"] = timeit(lambda: ops.head_forward_backward(eng.X[eng.n], pack.flat, pack.grad, eng.head_offs, y, eng.dfeat, eng.h1_buf, eng.dh1_buf, out, None, B, eng.F, eng.H1, eng.H2, eng.C, True))
     m = torch.zeros_like(pack.grad); v = torch.zeros_like(pack.grad); st = torch.ones(1, dtype=torch.int64, device="cuda")
+    res["fused_update"] = timeit(lambda: ops.fused_update(eng.dW32, eng.table, pack.flat, pack.grad, m, v, eng.shadow, eng.Wf, eng.Wd, st, None, 1e-3, 1e-4, 0.9, 0.999, 1e-7, eng.dense_off, pack.n_trainable))
     res["adam"] = timeit(lambda: ops.adam_step_(pack.trainable(), pack.grad, m, v, eng.shadow, st, None, 1e-3, 1e-4, 0.9, 0.999, 1e-7))
-    res["train_step(eager)"] = timeit(lambda: eng.train_step(x, y, out, augment=True), iters=5)
+    eng.step_ref = st
+    def full_step():
+        eng.train_step(x, y, out, augment=True)
+        eng.fused_update(m, v, st, None, cfg)
+    res["train_step(eager)"] = timeit(full_step, iters=5)
     # whole step as a CUDA graph
     side = torch.cuda.Stream()
     with torch.cuda.stream(side):
-        eng.train_step(x, y, out, augment=True)
+        full_step()
     torch.cuda.synchronize()
     gph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(gph):
-        eng.train_step(x, y, out, augment=True)
+        full_step()
     res["train_step(graph)"] = timeit(lambda: gph.replay(), iters=10)
     tot = sum(v for k, v in res.items() if not k.startswith("train_step") and not k.startswith("head(torch") and not k.startswith("make_theta"))
     for k, v in res.items():

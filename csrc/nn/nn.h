@@ -24,7 +24,7 @@ void conv_wgrad(const void* X, const void* DY, float* dW32, int B, int H, int W,
 void head_forward_backward(const void* feat, const float* W1, const float* b1, const float* W2, const float* b2,
                            const float* W3, const float* b3, const int64_t* y, float* gW1, float* gb1, float* gW2,
                            float* gb2, float* gW3, float* gb3, void* dfeat, float* h1_buf, float* dh1_buf,
-                           float* out, int B, int F, int H1, int H2, int C, int train, cudaStream_t st);
+                           float* out, int64_t* step, int B, int F, int H1, int H2, int C, int train, cudaStream_t st);
 void umma_shift_probe(const void* A, const void* Bm, float* out, int CK, int shift_rows, int mode, cudaStream_t st);
 
 // ---- data-movement kernels around the convolutions (nn_kernels.cu) ----
@@ -42,6 +42,9 @@ void unpool_relu(const void* g, const uint8_t* amax, const void* ypool, void* dY
                  int Wp, int Co, cudaStream_t st);
 void conv_weight_relayout(const void* shadow, const ConvLayerTable& t, void* Wf, void* Wd, cudaStream_t st);
 void conv_grad_finalize(float* dW32, const ConvLayerTable& t, float* grad, cudaStream_t st);
+void fused_update(float* dW32, const ConvLayerTable& t, float* flat, float* grad, float* m, float* v, void* shadow,
+                  void* Wf, void* Wd, const int64_t* step, const float* lr_scale, float lr, float decay, float beta1,
+                  float beta2, float eps, int64_t dense_off, int64_t n_trainable, cudaStream_t st);
 
 }  // namespace nn
 }  // namespace hefl

@@ -141,8 +141,8 @@ void unpool_relu(const Tensor& g, const Tensor& amax, const Tensor& ypool, Tenso
 
 // flat / grad are the ParamPack buffers; offs = [W1, b1, W2, b2, W3, b3] element offsets.
 void head_forward_backward(const Tensor& feat, const Tensor& flat, Tensor grad, at::IntArrayRef offs, const Tensor& y,
-                           Tensor dfeat, Tensor h1_buf, Tensor dh1_buf, Tensor out, int64_t B, int64_t F, int64_t H1,
-                           int64_t H2, int64_t C, bool train) {
+                           Tensor dfeat, Tensor h1_buf, Tensor dh1_buf, Tensor out, const c10::optional<Tensor>& step,
+                           int64_t B, int64_t F, int64_t H1, int64_t H2, int64_t C, bool train) {
   chk_bf16(feat, "feat"); chk_bf16(dfeat, "dfeat");
   TORCH_CHECK(offs.size() == 6, "need six parameter offsets");
   TORCH_CHECK(B <= 32 && B >= 1, "the head kernels handle up to 32 samples per step");
@@ -156,11 +156,27 @@ void head_forward_backward(const Tensor& feat, const Tensor& flat, Tensor grad, 
   hefl::nn::head_forward_backward(feat.data_ptr(), p + offs[0], p + offs[1], p + offs[2], p + offs[3], p + offs[4],
                                   p + offs[5], y.data_ptr<int64_t>(), g + offs[0], g + offs[1], g + offs[2],
                                   g + offs[3], g + offs[4], g + offs[5], dfeat.data_ptr(), h1_buf.data_ptr<float>(),
-                                  dh1_buf.data_ptr<float>(), out.data_ptr<float>(), (int)B, (int)F, (int)H1, (int)H2,
+                                  dh1_buf.data_ptr<float>(), out.data_ptr<float>(),
+                                  step.has_value() ? step->data_ptr<int64_t>() : nullptr, (int)B, (int)F, (int)H1, (int)H2,
                                   (int)C, train ? 1 : 0, cur());
 }
 
 void conv_set_debug(int64_t mask) { hefl::nn::conv_set_debug((int)mask); }
+
+hefl::nn::ConvLayerTable table_from(const Tensor& t);
+
+void fused_update(Tensor dW32, const Tensor& table, Tensor flat, Tensor grad, Tensor m, Tensor v, Tensor shadow, Tensor Wf,
+                  Tensor Wd, const Tensor& step, const c10::optional<Tensor>& lr_scale, double lr, double decay,
+                  double beta1, double beta2, double eps, int64_t dense_off, int64_t n_trainable) {
+  chk_bf16(shadow, "shadow"); chk_bf16(Wf, "Wf"); chk_bf16(Wd, "Wd");
+  TORCH_CHECK(flat.scalar_type() == at::kFloat && grad.scalar_type() == at::kFloat && m.scalar_type() == at::kFloat &&
+              v.scalar_type() == at::kFloat && dW32.scalar_type() == at::kFloat, "float32 buffers required");
+  TORCH_CHECK(step.is_cuda() && step.scalar_type() == at::kLong, "step must be a CUDA int64 tensor");
+  hefl::nn::fused_update(dW32.data_ptr<float>(), table_from(table), flat.data_ptr<float>(), grad.data_ptr<float>(),
+                         m.data_ptr<float>(), v.data_ptr<float>(), shadow.data_ptr(), Wf.data_ptr(), Wd.data_ptr(),
+                         step.data_ptr<int64_t>(), lr_scale.has_value() ? lr_scale->data_ptr<float>() : nullptr,
+                         (float)lr, (float)decay, (float)beta1, (float)beta2, (float)eps, dense_off, n_trainable, cur());
+}
 
 Tensor umma_shift_probe(const Tensor& A, const Tensor& Bm, int64_t CK, int64_t shift_rows, int64_t mode) {
   chk_bf16(A, "A"); chk_bf16(Bm, "Bm");
@@ -204,7 +220,8 @@ TORCH_LIBRARY_FRAGMENT(hefl, m) {
   m.def("conv_wgrad(Tensor X, Tensor DY, Tensor(a!) dW32, int B, int H, int W, int CK, int Co) -> ()", &conv_wgrad);
   m.def("preprocess_u8(Tensor x, Tensor? theta, Tensor(a!) X, int aug_seed, Tensor? step) -> ()", &preprocess_u8);
   m.def("unpool_relu(Tensor g, Tensor amax, Tensor ypool, Tensor(a!) dY, int B, int H, int W, int Co) -> ()", &unpool_relu);
-  m.def("head_forward_backward(Tensor feat, Tensor flat, Tensor(a!) grad, int[] offs, Tensor y, Tensor(b!) dfeat, Tensor(c!) h1_buf, Tensor(d!) dh1_buf, Tensor(e!) out, int B, int F, int H1, int H2, int C, bool train) -> ()", &head_forward_backward);
+  m.def("head_forward_backward(Tensor feat, Tensor flat, Tensor(a!) grad, int[] offs, Tensor y, Tensor(b!) dfeat, Tensor(c!) h1_buf, Tensor(d!) dh1_buf, Tensor(e!) out, Tensor(f!)? step, int B, int F, int H1, int H2, int C, bool train) -> ()", &head_forward_backward);
+  m.def("fused_update(Tensor(a!) dW32, Tensor table, Tensor(b!) flat, Tensor(c!) grad, Tensor(d!) m, Tensor(e!) v, Tensor(f!) shadow, Tensor(g!) Wf, Tensor(h!) Wd, Tensor step, Tensor? lr_scale, float lr, float decay, float beta1, float beta2, float eps, int dense_off, int n_trainable) -> ()", &fused_update);
   m.def("conv_set_debug(int mask) -> ()", &conv_set_debug);
   m.def("umma_shift_probe(Tensor A, Tensor Bm, int CK, int shift_rows, int mode) -> Tensor", &umma_shift_probe);
   m.def("conv_weight_relayout(Tensor shadow, Tensor table, Tensor(a!) Wf, Tensor(b!) Wd) -> ()", &conv_weight_relayout);

@@ -95,8 +95,11 @@ class LocalTrainer:
             loss.backward()
             self.out_train[0] = loss.detach()
             self.out_train[1] = (logits.argmax(1) == y).sum()
-        self.step_t += 1
         c = self.cfg
+        if self.engine is not None and self.engine.fused_step:
+            self.engine.fused_update(self.m, self.v, self.step_t, self.lr_scale, c)   # step counter bumped by the head kernel
+            return
+        self.step_t += 1
         self.ops.adam_step_(self.pack.trainable(), self.pack.grad, self.m, self.v,
                             self.engine.shadow if self.engine is not None else None,
                             self.step_t, self.lr_scale, c.lr, c.lr_decay, 0.9, 0.999, 1e-7)

@@ -149,6 +149,7 @@ def test_engine_gradients_match_autograd():
     # round the weights to bf16 so both paths see identical parameters
     pack.flat.copy_(pack.flat.to(torch.bfloat16).float())
     eng = MedCNNEngine(model, pack, cfg, dev)
+    eng.fused_step = False          # keep the gradients in pack.grad (the fused update consumes them in place)
     g = torch.Generator(device="cuda").manual_seed(7)
     x = torch.randint(0, 256, (8, 256, 256, 3), dtype=torch.uint8, device="cuda", generator=g)
     y = torch.randint(0, 2, (8,), device="cuda", generator=g)
@@ -185,3 +186,34 @@ def test_engine_gradients_match_autograd():
         rel = (a - b).abs().max().item() / denom
         cos = F.cosine_similarity(a, b, dim=0).item() if b.norm() > 0 else 1.0
         assert cos > 0.99 and rel < 0.25, (key, rel, cos)
+
+
+def test_fused_update_matches_separate_path():
+    """finalize+Adam+relayout in one launch == finalize -> adam_step_ -> relayout (three steps)."""
+    from hefl_b200.config import FLConfig
+    from hefl_b200.fl.trainer import LocalTrainer
+    from hefl_b200.models import ParamPack, create_model
+
+    def run(fused):
+        torch.manual_seed(1)
+        cfg = FLConfig(model="medcnn", batch_size=8, nn_backend="tcgen05")
+        dev = torch.device("cuda")
+        model = create_model("medcnn").to(dev)
+        pack = ParamPack(model)
+        tr = LocalTrainer(model, pack, cfg, dev, backend="tcgen05", use_graph=False, augment=False)
+        tr.engine.fused_step = fused
+        tr.engine.two_streams = fused
+        g = torch.Generator(device="cuda").manual_seed(3)
+        x = torch.randint(0, 256, (8, 256, 256, 3), dtype=torch.uint8, device="cuda", generator=g)
+        y = torch.randint(0, 2, (8,), device="cuda", generator=g)
+        for _ in range(3):
+            tr.train_step(x, y)
+        torch.cuda.synchronize()
+        return pack.flat.clone(), tr.engine.Wf.clone(), tr.engine.Wd.clone(), int(tr.step_t.item()), tr.out_train.clone()
+
+    a, b = run(True), run(False)
+    assert a[3] == b[3] == 3
+    assert (a[0] - b[0]).abs().max() < 2e-3        # fp32 atomics order differs between runs
+    assert (a[1].float() - b[1].float()).abs().max() < 2e-2
+    assert (a[2].float() - b[2].float()).abs().max() < 2e-2
+    assert abs(float(a[4][0]) - float(b[4][0])) < 5e-3

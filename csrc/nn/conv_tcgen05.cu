@@ -136,7 +136,7 @@ struct TapGemmCfg {
   static constexpr int NBUF_RAW = (BUDGET - W_BYTES - BAR_BYTES - 1024) / HALO;
   // ring depth beyond 3 and more than 2 TMEM tile buffers measured no gain; small footprints let a
   // wgrad CTA and a dgrad/forward CTA share an SM (the backward pass runs them on two streams)
-  static constexpr int NBUF = NBUF_RAW > 3 ? 3 : NBUF_RAW;
+  static constexpr int NBUF = NBUF_RAW > 2 ? 2 : NBUF_RAW;
   static constexpr int SMEM = W_BYTES + NBUF * HALO + BAR_BYTES + 1024;
   // TMEM tile buffers: the MMA -> epilogue -> MMA hand-off costs ~1500 cycles of mbarrier latency
   // (measured with all work disabled: 750 cycles/tile with 2 buffers), so small-channel layers use
@@ -146,13 +146,17 @@ struct TapGemmCfg {
   static constexpr int ACC_COLS = NT * NACC * CO;
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
   static_assert(NT >= 2, "need at least two TMEM tile buffers");
+  // two CTAs per SM when shared memory and TMEM allow: the kernels are latency-bound (issue, TMA,
+  // mbarrier hand-offs), so more independent pipelines on the same SM fill the bubbles
+  static constexpr int OCC = (3 * SMEM <= 226 * 1024 && 3 * TMEM_COLS <= 512) ? 3
+                             : ((2 * SMEM <= 226 * 1024 && 2 * TMEM_COLS <= 512) ? 2 : 1);
   static_assert(NBUF >= 1, "halo tile does not fit in shared memory");
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
   static_assert(CO % 32 == 0 && CO <= 128, "CO must be 32, 64, 96 or 128");
 };
 
 template <int CK, int CO, bool POOL>
-__global__ void __launch_bounds__(608, 1)
+__global__ void __launch_bounds__(352, TapGemmCfg<CK, CO, POOL>::OCC)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                 const TapGemmArgs a) {
   using Cfg = TapGemmCfg<CK, CO, POOL>;
@@ -171,22 +175,22 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 16 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmW);
     // POOL: two MMA-issuing warps (one per accumulator) => 2 commits per buffer / tile
     for (int s = 0; s < Cfg::NBUF; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], Cfg::NACC); }
     mbar_init(wfull, 1);
-    for (int i = 0; i < Cfg::NT; ++i) { mbar_init(&tfull[i], Cfg::NACC); mbar_init(&tempty[i], 16); }
+    for (int i = 0; i < Cfg::NT; ++i) { mbar_init(&tfull[i], Cfg::NACC); mbar_init(&tempty[i], 8); }
     fence_barrier_init();
   }
-  if (warp == 17) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 9) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 16) {
+  if (warp == 8) {
     // ===== TMA producer =====
     if (elect_one()) {
       mbar_expect_tx(wfull, Cfg::W_BYTES);
@@ -224,10 +228,10 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (++buf == Cfg::NBUF) { buf = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 17 || warp == 18) {
+  } else if (warp == 9 || warp == 10) {
     // ===== MMA issuers: warp 9 owns accumulator 0, warp 10 accumulator 1 (the small-N MMAs of these
     // layers are bound by per-thread issue cost, not by the tensor core, so two issuers run in parallel)
-    const int jme = warp - 17;
+    const int jme = warp - 9;
     if (jme >= Cfg::NACC) goto done_roles;
     constexpr uint32_t idesc = make_idesc_bf16(128, CO);
     mbar_wait(wfull, 0);
@@ -273,9 +277,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (++tb == Cfg::NT) { tb = 0; tb_phase ^= 1; }
     }
   } else {
-    // ===== epilogue warps (0..15): quadrant = warp % 4, channel slice = warp / 4 (8 channels a time).
-    // The small-channel layers are bound by the epilogue's instruction latency, so it is spread over
-    // 16 warps (measured: 8 warps x 16 channels = 55 us on layer 1).
+    // ===== epilogue warps (0..7): quadrant = warp % 4, channel slice = warp / 4 (8 channels a time).
+    // (16 epilogue warps measured no faster than 8; 8 keeps the CTA small enough for 2 CTAs per SM.)
     const int qd = warp & 3;                       // TMEM lane quadrant this warp may read
     const int grp = warp >> 2;
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
@@ -294,7 +297,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int wp = col >> 1;
         const bool writer = ((lane & 1) == 0) && wp < a.Wp;
 #pragma unroll 1
-        for (int ch = grp; ch < ((a.dbg & 4) ? 0 : CO / 8); ch += 4) {
+        for (int ch = grp; ch < ((a.dbg & 4) ? 0 : CO / 8); ch += 2) {
           float v0[8], v1[8];
           tmem_ld8_nowait(tmem_base + lane_base + (tb * 2 + 0) * CO + ch * 8, v0);
           tmem_ld8_nowait(tmem_base + lane_base + (tb * 2 + 1) * CO + ch * 8, v1);
@@ -337,7 +340,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       } else {
         const int m = t * 128 + qd * 32 + lane;
 #pragma unroll 1
-        for (int ch = grp; ch < CO / 8; ch += 4) {
+        for (int ch = grp; ch < CO / 8; ch += 2) {
           float v[8];
           tmem_ld8_nowait(tmem_base + lane_base + tb * CO + ch * 8, v);
           tmem_ld_wait();
@@ -357,7 +360,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 done_roles:
   tc_fence_before();
   __syncthreads();
-  if (warp == 17) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
@@ -371,10 +374,11 @@ static void launch_tap_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Wt, Tap
   auto kern = tap_gemm_kernel<CK, CO, POOL>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   const int ny = a.co_total / CO;
-  int gx = a.num_tiles < num_sms() / ny ? a.num_tiles : num_sms() / ny;
+  const int slots = num_sms() * Cfg::OCC / ny;
+  int gx = a.num_tiles < slots ? a.num_tiles : slots;
   if (gx < 1) gx = 1;
   dim3 grid(gx, ny);
-  kern<<<grid, 608, Cfg::SMEM, st>>>(tmA, tmW, a);
+  kern<<<grid, 352, Cfg::SMEM, st>>>(tmA, tmW, a);
   hefl::cuda::note_launch();
 }
 
@@ -472,18 +476,19 @@ struct WgradCfg {
   // deep ring: stages are small (one X row segment + one dY chunk), so the number of bytes in
   // flight, not the MMA rate, bounds throughput (measured: 6 stages -> 204 us on layer 1)
   static constexpr int NSTAGE_RAW = (200 * 1024 - ONES_BYTES) / STAGE_FULL;
-  static constexpr int NSTAGE = NSTAGE_RAW > 8 ? 8 : NSTAGE_RAW;
+  static constexpr int NSTAGE = NSTAGE_RAW > 6 ? 6 : NSTAGE_RAW;
   static constexpr int SMEM = NSTAGE * STAGE_FULL + ONES_BYTES + 512 + 1024;
   static constexpr int COLS = (NACC + 1) * COT;                // + bias accumulator
   static_assert(NSTAGE >= 4, "ring needs 3 live stages + 1 in flight");
   static constexpr int TMEM_COLS = COLS <= 32 ? 32 : (COLS <= 64 ? 64 : (COLS <= 128 ? 128 : (COLS <= 256 ? 256 : 512)));
   static_assert(COLS <= 512, "accumulators exceed TMEM");
+  static constexpr int OCC = (2 * SMEM <= 226 * 1024 && 2 * TMEM_COLS <= 512) ? 2 : 1;   // CTAs per SM
   static_assert(CK == 16 || CK == 32 || CK == 64, "CK must be one swizzle atom");
   static_assert(COT == 32 || COT == 64, "COT must be one swizzle atom");
 };
 
 template <int CK, int COT, bool FLAT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, WgradCfg<CK, COT, FLAT>::OCC)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
              const WgradArgs a) {
   using Cfg = WgradCfg<CK, COT, FLAT>;
@@ -749,7 +754,7 @@ static void launch_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* DY, int B,
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   // every CTA pays a fixed epilogue (fp32 RED of all accumulators): give each at least a few steps
   int gx = total_steps / (FLAT ? 6 : 24);
-  if (gx > num_sms() / cot) gx = num_sms() / cot;
+  if (gx > num_sms() * Cfg::OCC / cot) gx = num_sms() * Cfg::OCC / cot;
   if (gx > (FLAT ? a.nchunks : a.units)) gx = FLAT ? a.nchunks : a.units;
   if (gx < 1) gx = 1;
   dim3 grid(gx, cot);

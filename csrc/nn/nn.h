@@ -25,6 +25,14 @@ void head_forward_backward(const void* feat, const float* W1, const float* b1, c
                            const float* W3, const float* b3, const int64_t* y, float* gW1, float* gb1, float* gW2,
                            float* gb2, float* gW3, float* gb3, void* dfeat, float* h1_buf, float* dh1_buf,
                            float* out, int64_t* step, int B, int F, int H1, int H2, int C, int train, cudaStream_t st);
+// ---- ResNet building blocks (resnet_kernels.cu) ----
+void bn_forward(const void* x, const void* res, const float* gamma, const float* beta, float* run_mean, float* run_var,
+                float* mean, float* invstd, float* sums, void* y, int64_t P, int C, float momentum, float eps, int relu,
+                cudaStream_t st);
+void bn_backward(const void* dy, const void* x, const void* y, const float* mean, const float* invstd,
+                 const float* gamma, float* sums, void* dx, void* dres, int64_t P, int C, int relu, cudaStream_t st);
+void avgpool_forward(const void* x, float* out, int B, int HW, int C, cudaStream_t st);
+void avgpool_backward(const float* dout, void* dx, int B, int HW, int C, cudaStream_t st);
 void umma_shift_probe(const void* A, const void* Bm, float* out, int CK, int shift_rows, int mode, cudaStream_t st);
 
 // ---- data-movement kernels around the convolutions (nn_kernels.cu) ----

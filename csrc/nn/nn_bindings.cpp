@@ -165,6 +165,47 @@ void conv_set_debug(int64_t mask) { hefl::nn::conv_set_debug((int)mask); }
 
 hefl::nn::ConvLayerTable table_from(const Tensor& t);
 
+// x, res, y: NHWC bf16 viewed as [P, C]. Returns nothing; mean/invstd/sums are caller-provided fp32 scratch.
+void bn_forward(const Tensor& x, const c10::optional<Tensor>& res, const Tensor& gamma, const Tensor& beta,
+                const c10::optional<Tensor>& run_mean, const c10::optional<Tensor>& run_var, Tensor mean, Tensor invstd,
+                Tensor sums, Tensor y, double momentum, double eps, bool relu) {
+  chk_bf16(x, "x"); chk_bf16(y, "y");
+  const int64_t C = gamma.numel();
+  TORCH_CHECK(C % 8 == 0 && x.numel() % C == 0, "C must be a multiple of 8");
+  const int64_t P = x.numel() / C;
+  TORCH_CHECK(mean.numel() >= C && invstd.numel() >= C && sums.numel() >= 2 * C, "scratch too small");
+  const void* rp = nullptr;
+  if (res.has_value()) { chk_bf16(*res, "res"); TORCH_CHECK(res->numel() == x.numel(), "residual shape"); rp = res->data_ptr(); }
+  hefl::nn::bn_forward(x.data_ptr(), rp, gamma.data_ptr<float>(), beta.data_ptr<float>(),
+                       run_mean.has_value() ? run_mean->data_ptr<float>() : nullptr,
+                       run_var.has_value() ? run_var->data_ptr<float>() : nullptr, mean.data_ptr<float>(),
+                       invstd.data_ptr<float>(), sums.data_ptr<float>(), y.data_ptr(), P, (int)C, (float)momentum,
+                       (float)eps, relu ? 1 : 0, cur());
+}
+
+void bn_backward(const Tensor& dy, const Tensor& x, const Tensor& y, const Tensor& mean, const Tensor& invstd,
+                 const Tensor& gamma, Tensor sums, Tensor dx, const c10::optional<Tensor>& dres, bool relu) {
+  chk_bf16(dy, "dy"); chk_bf16(x, "x"); chk_bf16(y, "y"); chk_bf16(dx, "dx");
+  const int64_t C = gamma.numel();
+  const int64_t P = x.numel() / C;
+  void* dr = nullptr;
+  if (dres.has_value()) { chk_bf16(*dres, "dres"); dr = dres->data_ptr(); }
+  hefl::nn::bn_backward(dy.data_ptr(), x.data_ptr(), y.data_ptr(), mean.data_ptr<float>(), invstd.data_ptr<float>(),
+                        gamma.data_ptr<float>(), sums.data_ptr<float>(), dx.data_ptr(), dr, P, (int)C, relu ? 1 : 0, cur());
+}
+
+void avgpool_forward(const Tensor& x, Tensor out, int64_t B, int64_t HW, int64_t C) {
+  chk_bf16(x, "x");
+  TORCH_CHECK(x.numel() == B * HW * C && out.numel() == B * C && out.scalar_type() == at::kFloat, "shape mismatch");
+  hefl::nn::avgpool_forward(x.data_ptr(), out.data_ptr<float>(), (int)B, (int)HW, (int)C, cur());
+}
+
+void avgpool_backward(const Tensor& dout, Tensor dx, int64_t B, int64_t HW, int64_t C) {
+  chk_bf16(dx, "dx");
+  TORCH_CHECK(dx.numel() == B * HW * C && dout.numel() == B * C && dout.scalar_type() == at::kFloat, "shape mismatch");
+  hefl::nn::avgpool_backward(dout.data_ptr<float>(), dx.data_ptr(), (int)B, (int)HW, (int)C, cur());
+}
+
 void fused_update(Tensor dW32, const Tensor& table, Tensor flat, Tensor grad, Tensor m, Tensor v, Tensor shadow, Tensor Wf,
                   Tensor Wd, const Tensor& step, const c10::optional<Tensor>& lr_scale, double lr, double decay,
                   double beta1, double beta2, double eps, int64_t dense_off, int64_t n_trainable) {
@@ -223,6 +264,10 @@ TORCH_LIBRARY_FRAGMENT(hefl, m) {
   m.def("head_forward_backward(Tensor feat, Tensor flat, Tensor(a!) grad, int[] offs, Tensor y, Tensor(b!) dfeat, Tensor(c!) h1_buf, Tensor(d!) dh1_buf, Tensor(e!) out, Tensor(f!)? step, int B, int F, int H1, int H2, int C, bool train) -> ()", &head_forward_backward);
   m.def("fused_update(Tensor(a!) dW32, Tensor table, Tensor(b!) flat, Tensor(c!) grad, Tensor(d!) m, Tensor(e!) v, Tensor(f!) shadow, Tensor(g!) Wf, Tensor(h!) Wd, Tensor step, Tensor? lr_scale, float lr, float decay, float beta1, float beta2, float eps, int dense_off, int n_trainable) -> ()", &fused_update);
   m.def("conv_set_debug(int mask) -> ()", &conv_set_debug);
+  m.def("bn_forward(Tensor x, Tensor? res, Tensor gamma, Tensor beta, Tensor(a!)? run_mean, Tensor(b!)? run_var, Tensor(c!) mean, Tensor(d!) invstd, Tensor(e!) sums, Tensor(f!) y, float momentum, float eps, bool relu) -> ()", &bn_forward);
+  m.def("bn_backward(Tensor dy, Tensor x, Tensor y, Tensor mean, Tensor invstd, Tensor gamma, Tensor(a!) sums, Tensor(b!) dx, Tensor(c!)? dres, bool relu) -> ()", &bn_backward);
+  m.def("avgpool_forward(Tensor x, Tensor(a!) out, int B, int HW, int C) -> ()", &avgpool_forward);
+  m.def("avgpool_backward(Tensor dout, Tensor(a!) dx, int B, int HW, int C) -> ()", &avgpool_backward);
   m.def("umma_shift_probe(Tensor A, Tensor Bm, int CK, int shift_rows, int mode) -> Tensor", &umma_shift_probe);
   m.def("conv_weight_relayout(Tensor shadow, Tensor table, Tensor(a!) Wf, Tensor(b!) Wd) -> ()", &conv_weight_relayout);
   m.def("conv_grad_finalize(Tensor(a!) dW32, Tensor table, Tensor(b!) grad) -> ()", &conv_grad_finalize);

@@ -1,0 +1,252 @@
+// ResNet building blocks for sm_100a: training-mode BatchNorm over NHWC bf16 with
+// fused residual add and ReLU (forward and backward), and global average pooling. Activations are
+// [P = B*H*W pixels, C channels] bf16, statistics and parameters fp32.
+//
+//   forward : bn_stats (per-channel sum / sum-of-squares, one fp32 atomic per channel per CTA)
+//             bn_apply (normalise, scale/shift, + residual, ReLU; updates running statistics)
+//   backward: bn_bwd_reduce (dbeta, dgamma with the ReLU mask recomputed from the output)
+//             bn_bwd_apply  (dx, and the gradient that flows into the residual branch)
+#include <cuda_bf16.h>
+
+#include "../he/kernels.h"
+#include "nn.h"
+
+namespace hefl {
+namespace nn {
+
+// Each CTA reduces a slab of rows for 8-channel groups; threads = (row lane, channel group).
+__global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums, int64_t P, int C) {
+  const int groups = C >> 3;
+  const int cg = threadIdx.x % groups;
+  const int rl = threadIdx.x / groups;
+  const int rows_per_iter = blockDim.x / groups;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * rows_per_iter + rl; r < P; r += (int64_t)gridDim.x * rows_per_iter) {
+    const uint4 v = *reinterpret_cast<const uint4*>(x + r * C + cg * 8);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float a = __uint_as_float(w[i] << 16), b = __uint_as_float(w[i] & 0xFFFF0000u);
+      s[2 * i] += a; q[2 * i] += a * a;
+      s[2 * i + 1] += b; q[2 * i + 1] += b * b;
+    }
+  }
+  extern __shared__ float red[];   // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    atomicAdd(&red[cg * 8 + i], s[i]);
+    atomicAdd(&red[C + cg * 8 + i], q[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], red[i]);
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, float* __restrict__ mean, float* __restrict__ invstd,
+                                   float* __restrict__ run_mean, float* __restrict__ run_var, int64_t P, int C,
+                                   float momentum, float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float m = sums[c] / (float)P;
+  const float var = fmaxf(sums[C + c] / (float)P - m * m, 0.f);
+  mean[c] = m;
+  invstd[c] = rsqrtf(var + eps);
+  if (run_mean) {
+    run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * m;
+    run_var[c] = (1.f - momentum) * run_var[c] + momentum * var * ((float)P / (float)(P > 1 ? P - 1 : 1));
+  }
+}
+
+__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                __nv_bfloat16* __restrict__ y, int64_t P, int C, int relu) {
+  const int groups = C >> 3;
+  const int64_t total = P * groups;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(t % groups);
+    const int64_t o = (t / groups) * C + cg * 8;
+    const uint4 v = *reinterpret_cast<const uint4*>(x + o);
+    uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+    if (res) rv = *reinterpret_cast<const uint4*>(res + o);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a[2] = {__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xFFFF0000u)};
+      const float r[2] = {__uint_as_float(rw[i] << 16), __uint_as_float(rw[i] & 0xFFFF0000u)};
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = cg * 8 + 2 * i + j;
+        float z = (a[j] - mean[c]) * invstd[c] * gamma[c] + beta[c] + r[j];
+        if (relu) z = z > 0.f ? z : 0.f;
+        a[j] = z;
+      }
+      const __nv_bfloat162 pk = __floats2bfloat162_rn(a[0], a[1]);
+      ow[i] = *reinterpret_cast<const uint32_t*>(&pk);
+    }
+    *reinterpret_cast<uint4*>(y + o) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+}
+
+// sums[0..C) = dbeta = sum dy', sums[C..2C) = dgamma = sum dy' * xhat, with dy' = dy * (y > 0) if relu.
+__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, float* __restrict__ sums, int64_t P, int C,
+                                     int relu) {
+  const int groups = C >> 3;
+  const int cg = threadIdx.x % groups;
+  const int rl = threadIdx.x / groups;
+  const int rows_per_iter = blockDim.x / groups;
+  float s[8], q[8], mu[8], is[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = q[i] = 0.f; mu[i] = mean[cg * 8 + i]; is[i] = invstd[cg * 8 + i]; }
+  for (int64_t r = (int64_t)blockIdx.x * rows_per_iter + rl; r < P; r += (int64_t)gridDim.x * rows_per_iter) {
+    const int64_t o = r * C + cg * 8;
+    const uint4 dv = *reinterpret_cast<const uint4*>(dy + o);
+    const uint4 xv = *reinterpret_cast<const uint4*>(x + o);
+    uint4 yv = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    if (relu) yv = *reinterpret_cast<const uint4*>(y + o);
+    const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, xw[4] = {xv.x, xv.y, xv.z, xv.w}, yw[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int k = 2 * i + j;
+        const uint32_t sh = j ? 0u : 16u;
+        const float d = __uint_as_float(j ? (dw[i] & 0xFFFF0000u) : (dw[i] << 16));
+        const float xx = __uint_as_float(j ? (xw[i] & 0xFFFF0000u) : (xw[i] << 16));
+        const uint32_t yb = j ? (yw[i] >> 16) : (yw[i] & 0xFFFFu);
+        (void)sh;
+        const bool on = !relu || (yb != 0u && (yb & 0x8000u) == 0u);
+        const float dd = on ? d : 0.f;
+        s[k] += dd;
+        q[k] += dd * (xx - mu[k]) * is[k];
+      }
+    }
+  }
+  extern __shared__ float red[];
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    atomicAdd(&red[cg * 8 + i], s[i]);
+    atomicAdd(&red[C + cg * 8 + i], q[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], red[i]);
+}
+
+// dx = gamma*invstd * (dy' - dbeta/P - xhat*dgamma/P); dres = dy' (gradient into the residual branch).
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                    const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ sums, __nv_bfloat16* __restrict__ dx,
+                                    __nv_bfloat16* __restrict__ dres, int64_t P, int C, int relu) {
+  const int groups = C >> 3;
+  const int64_t total = P * groups;
+  const float invP = 1.f / (float)P;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(t % groups);
+    const int64_t o = (t / groups) * C + cg * 8;
+    const uint4 dv = *reinterpret_cast<const uint4*>(dy + o);
+    const uint4 xv = *reinterpret_cast<const uint4*>(x + o);
+    uint4 yv = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    if (relu) yv = *reinterpret_cast<const uint4*>(y + o);
+    const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, xw[4] = {xv.x, xv.y, xv.z, xv.w}, yw[4] = {yv.x, yv.y, yv.z, yv.w};
+    uint32_t ow[4], rw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float od[2], rd[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = cg * 8 + 2 * i + j;
+        const float d = __uint_as_float(j ? (dw[i] & 0xFFFF0000u) : (dw[i] << 16));
+        const float xx = __uint_as_float(j ? (xw[i] & 0xFFFF0000u) : (xw[i] << 16));
+        const uint32_t yb = j ? (yw[i] >> 16) : (yw[i] & 0xFFFFu);
+        const bool on = !relu || (yb != 0u && (yb & 0x8000u) == 0u);
+        const float dd = on ? d : 0.f;
+        const float xh = (xx - mean[c]) * invstd[c];
+        od[j] = gamma[c] * invstd[c] * (dd - sums[c] * invP - xh * sums[C + c] * invP);
+        rd[j] = dd;
+      }
+      const __nv_bfloat162 p0 = __floats2bfloat162_rn(od[0], od[1]);
+      const __nv_bfloat162 p1 = __floats2bfloat162_rn(rd[0], rd[1]);
+      ow[i] = *reinterpret_cast<const uint32_t*>(&p0);
+      rw[i] = *reinterpret_cast<const uint32_t*>(&p1);
+    }
+    *reinterpret_cast<uint4*>(dx + o) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    if (dres) *reinterpret_cast<uint4*>(dres + o) = make_uint4(rw[0], rw[1], rw[2], rw[3]);
+  }
+}
+
+static inline int blocks_for(int64_t work, int per_block, int cap) {
+  int64_t b = (work + per_block - 1) / per_block;
+  if (b > cap) b = cap;
+  return b < 1 ? 1 : (int)b;
+}
+
+void bn_forward(const void* x, const void* res, const float* gamma, const float* beta, float* run_mean, float* run_var,
+                float* mean, float* invstd, float* sums, void* y, int64_t P, int C, float momentum, float eps, int relu,
+                cudaStream_t st) {
+  cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), st);
+  const int threads = 256 - 256 % (C / 8 > 256 ? 256 : (C / 8));   // multiple of the channel-group count
+  const int rows_per_iter = threads / (C / 8);
+  bn_stats_kernel<<<blocks_for(P, rows_per_iter * 8, 148 * 4), threads, 2 * C * 4, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), sums, P, C);
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, mean, invstd, run_mean, run_var, P, C, momentum, eps);
+  bn_apply_kernel<<<blocks_for(P * (C / 8), 256, 148 * 16), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(res), mean, invstd, gamma, beta,
+      reinterpret_cast<__nv_bfloat16*>(y), P, C, relu);
+  hefl::cuda::note_launch(3);
+}
+
+void bn_backward(const void* dy, const void* x, const void* y, const float* mean, const float* invstd,
+                 const float* gamma, float* sums, void* dx, void* dres, int64_t P, int C, int relu, cudaStream_t st) {
+  cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), st);
+  const int threads = 256 - 256 % (C / 8 > 256 ? 256 : (C / 8));
+  const int rows_per_iter = threads / (C / 8);
+  bn_bwd_reduce_kernel<<<blocks_for(P, rows_per_iter * 8, 148 * 4), threads, 2 * C * 4, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x),
+      reinterpret_cast<const __nv_bfloat16*>(y), mean, invstd, sums, P, C, relu);
+  bn_bwd_apply_kernel<<<blocks_for(P * (C / 8), 256, 148 * 16), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x),
+      reinterpret_cast<const __nv_bfloat16*>(y), mean, invstd, gamma, sums, reinterpret_cast<__nv_bfloat16*>(dx),
+      reinterpret_cast<__nv_bfloat16*>(dres), P, C, relu);
+  hefl::cuda::note_launch(2);
+}
+
+// Global average pool over HW: x [B, HW, C] bf16 -> out [B, C] fp32 (forward) and the broadcast back.
+__global__ void avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int HW, int C) {
+  const int b = blockIdx.y;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int p = 0; p < HW; ++p) acc += __bfloat162float(x[((int64_t)b * HW + p) * C + c]);
+    out[b * C + c] = acc / (float)HW;
+  }
+}
+__global__ void avgpool_bwd_kernel(const float* __restrict__ dout, __nv_bfloat16* __restrict__ dx, int HW, int C,
+                                   int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t b = i / ((int64_t)HW * C);
+    dx[i] = __float2bfloat16(dout[b * C + c] / (float)HW);
+  }
+}
+void avgpool_forward(const void* x, float* out, int B, int HW, int C, cudaStream_t st) {
+  dim3 grid((C + 127) / 128, B);
+  avgpool_fwd_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, HW, C);
+  hefl::cuda::note_launch();
+}
+void avgpool_backward(const float* dout, void* dx, int B, int HW, int C, cudaStream_t st) {
+  const int64_t total = (int64_t)B * HW * C;
+  avgpool_bwd_kernel<<<blocks_for(total, 256, 148 * 8), 256, 0, st>>>(dout, reinterpret_cast<__nv_bfloat16*>(dx), HW, C, total);
+  hefl::cuda::note_launch();
+}
+
+}  // namespace nn
+}  // namespace hefl

@@ -41,6 +41,7 @@ CUDA_SOURCES = [
     "comm/allreduce_modq.cu",
     "nn/conv_tcgen05.cu",
     "nn/nn_kernels.cu",
+    "nn/resnet_kernels.cu",
 ]
 HOST_SOURCES = [
     "he/host_math.cpp",

@@ -1,5 +1,6 @@
 """ResNet-18 / ResNet-50 (BASELINE.json configs[2], configs[4]) written against plain
-torch.nn so there is no torchvision dependency. BatchNorm running statistics are part of the
+torch.nn so there is no torchvision dependency. BatchNorm(+residual)+ReLU and the global average
+pool run on the fused sm_100a kernels of ``ops/resnet_ops.py`` when activations are NHWC bf16. BatchNorm running statistics are part of the
 federated state (Keras ``get_weights`` includes moving mean/variance, FLPyfhelin.py:151)."""
 from __future__ import annotations
 
@@ -8,6 +9,8 @@ from typing import List, Optional, Tuple, Type
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+from ..ops.resnet_ops import bn_act, global_avgpool
 
 
 class BasicBlock(nn.Module):
@@ -24,10 +27,9 @@ class BasicBlock(nn.Module):
             self.down = nn.Sequential(nn.Conv2d(cin, planes, 1, stride, bias=False), nn.BatchNorm2d(planes))
 
     def forward(self, x):
-        idt = x if self.down is None else self.down(x)
-        out = F.relu(self.bn1(self.conv1(x)))
-        out = self.bn2(self.conv2(out))
-        return F.relu(out + idt)
+        idt = x if self.down is None else bn_act(self.down[1], self.down[0](x), relu=False)
+        out = bn_act(self.bn1, self.conv1(x))
+        return bn_act(self.bn2, self.conv2(out), res=idt)      # relu(bn(.) + identity) in one kernel
 
 
 class Bottleneck(nn.Module):
@@ -46,11 +48,10 @@ class Bottleneck(nn.Module):
             self.down = nn.Sequential(nn.Conv2d(cin, planes * 4, 1, stride, bias=False), nn.BatchNorm2d(planes * 4))
 
     def forward(self, x):
-        idt = x if self.down is None else self.down(x)
-        out = F.relu(self.bn1(self.conv1(x)))
-        out = F.relu(self.bn2(self.conv2(out)))
-        out = self.bn3(self.conv3(out))
-        return F.relu(out + idt)
+        idt = x if self.down is None else bn_act(self.down[1], self.down[0](x), relu=False)
+        out = bn_act(self.bn1, self.conv1(x))
+        out = bn_act(self.bn2, self.conv2(out))
+        return bn_act(self.bn3, self.conv3(out), res=idt)
 
 
 class ResNet(nn.Module):
@@ -76,10 +77,9 @@ class ResNet(nn.Module):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
 
     def forward(self, x):
-        x = F.max_pool2d(F.relu(self.bn1(self.conv1(x))), 3, 2, 1)
+        x = F.max_pool2d(bn_act(self.bn1, self.conv1(x)), 3, 2, 1)
         x = self.stages(x)
-        x = F.adaptive_avg_pool2d(x, 1).flatten(1)
-        return self.fc(x)
+        return self.fc(global_avgpool(x))
 
     def keras_layers(self) -> List[Tuple[str, Optional[nn.Module]]]:
         """One entry per weight-bearing module, in definition order."""

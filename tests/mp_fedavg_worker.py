@@ -1,0 +1,73 @@
+"""Multi-process worker: one full encrypted-FedAvg round through FederatedRunner on every rank;
+checks that the decrypted aggregate equals the plaintext mean of the ranks' locally trained weights
+and that all ranks end with identical models. gloo (CPU) or nccl (one GPU per rank)."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from hefl_b200.config import FLConfig  # noqa: E402
+from hefl_b200.fl import FederatedRunner  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--backend", default="gloo")
+    ap.add_argument("--model", default="cnn2")
+    ap.add_argument("--transport", default=None)
+    ap.add_argument("--rounds", type=int, default=2)
+    args = ap.parse_args()
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+    gpu = args.backend == "nccl"
+    if gpu:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        device = torch.device("cuda", torch.cuda.current_device())
+        dist.init_process_group("nccl", device_id=device)
+    else:
+        device = torch.device("cpu")
+        dist.init_process_group("gloo")
+    if args.model == "medcnn":
+        cfg = FLConfig(model="medcnn", local_epochs=1, steps_per_epoch=2, val_steps=1, clients=world,
+                       nn_backend="tcgen05" if gpu else "cudnn", transport=args.transport or "fused",
+                       device="cuda" if gpu else "cpu")
+    else:
+        cfg = FLConfig(model="cnn2", image_size=28, in_channels=1, num_classes=10, batch_size=8, local_epochs=1,
+                       steps_per_epoch=2, val_steps=1, clients=world, he_preset="n4096_l3", nn_backend="cudnn",
+                       dtype="bf16" if gpu else "fp32", transport=args.transport or ("fused" if gpu else "gloo"),
+                       device="cuda" if gpu else "cpu")
+    run = FederatedRunner(cfg, rank=rank, world=world, device=device)
+    worst = 0.0
+    for rnd in range(args.rounds):
+        run.local_train()
+        mine = run.pack.flat.clone()
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        plain_mean = torch.stack(gathered).mean(0)
+        ct = run.encrypt_update()
+        agg = run.aggregate(ct)
+        run.decrypt_apply(agg)
+        run.guard_finite()
+        if hasattr(run.transport, "check_status"):
+            run.transport.check_status()
+        err = float((run.pack.flat - plain_mean).abs().max())
+        worst = max(worst, err)
+        # every rank must hold the same global model after the round
+        ref = run.pack.flat.clone()
+        dist.broadcast(ref, src=0)
+        assert torch.equal(ref, run.pack.flat), "ranks diverged"
+        run.round += 1
+    t = torch.tensor([worst], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print("MP_REPORT " + json.dumps({"world": world, "backend": args.backend, "transport": run.transport.name,
+                                         "rounds": args.rounds, "max_abs_err": float(t), "n_ct": run.n_ct}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,105 @@
+"""Fused BatchNorm(+residual)+ReLU and global average pool kernels vs plain PyTorch fp32
+references of the same ops, and a ResNet-18 step with the fused path on/off."""
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+@pytest.mark.parametrize("shape", [(8, 64, 16, 16), (4, 128, 7, 9), (2, 24, 5, 5), (3, 512, 4, 4)])
+@pytest.mark.parametrize("with_res,relu", [(False, True), (True, True), (False, False)])
+def test_bn_act_matches_fp32_reference(shape, with_res, relu):
+    from hefl_b200.ops import resnet_ops
+    torch.manual_seed(0)
+    B, C, H, W = shape
+    dev = "cuda"
+    x = _cl((torch.randn(shape, device=dev) * 1.5 + 0.3).to(torch.bfloat16))
+    res = _cl(torch.randn(shape, device=dev).to(torch.bfloat16)) if with_res else None
+    bn = nn.BatchNorm2d(C).to(dev)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.uniform_(-0.5, 0.5)
+    bn_ref = nn.BatchNorm2d(C).to(dev)
+    bn_ref.load_state_dict(bn.state_dict())
+    g = _cl(torch.randn(shape, device=dev).to(torch.bfloat16))
+
+    xa = x.clone().requires_grad_(True)
+    ra = res.clone().requires_grad_(True) if with_res else None
+    y = resnet_ops.bn_act(bn, xa, ra, relu)
+    assert y.dtype == torch.bfloat16 and y.is_contiguous(memory_format=torch.channels_last)
+    y.backward(g)
+
+    xb = x.float().requires_grad_(True)
+    rb = res.float().requires_grad_(True) if with_res else None
+    z = bn_ref(xb)
+    if with_res:
+        z = z + rb
+    if relu:
+        # the kernel masks with the bf16-rounded output; emulate that rounding for the mask
+        z = torch.where(z.to(torch.bfloat16) > 0, z, torch.zeros_like(z))
+    z.backward(g.float())
+
+    assert torch.allclose(y.float(), z, atol=3e-2, rtol=2e-2)
+    def close(a, b, tol):
+        return (a.float() - b).norm() / (b.norm() + 1e-12) < tol
+    assert close(xa.grad, xb.grad, 2e-2)
+    if with_res:
+        assert close(ra.grad, rb.grad, 1e-2)
+    assert close(bn.weight.grad, bn_ref.weight.grad, 1e-2)
+    assert close(bn.bias.grad, bn_ref.bias.grad, 1e-2)
+    assert torch.allclose(bn.running_mean, bn_ref.running_mean, atol=1e-3)
+    assert torch.allclose(bn.running_var, bn_ref.running_var, atol=2e-3, rtol=1e-3)
+    assert int(bn.num_batches_tracked) == 1
+
+
+def test_global_avgpool_matches_reference():
+    from hefl_b200.ops import resnet_ops
+    x = _cl(torch.randn(5, 96, 7, 7, device="cuda").to(torch.bfloat16)).requires_grad_(True)
+    out = resnet_ops.global_avgpool(x)
+    ref = x.detach().float().mean((2, 3))
+    assert out.dtype == torch.float32 and torch.allclose(out, ref, atol=1e-5)
+    g = torch.randn_like(out)
+    out.backward(g)
+    assert torch.allclose(x.grad.float(), (g / 49)[:, :, None, None].expand(5, 96, 7, 7), atol=1e-3, rtol=1e-2)
+
+
+def test_resnet18_step_fused_vs_aten():
+    from hefl_b200 import _ext
+    from hefl_b200.models import create_model
+    from hefl_b200.ops import resnet_ops
+    ops = _ext.ops()
+    torch.manual_seed(1)
+    m1 = create_model("resnet18", num_classes=10).cuda().train()
+    m2 = create_model("resnet18", num_classes=10).cuda().train()
+    m2.load_state_dict(m1.state_dict())
+    x = torch.randn(8, 64, 64, 3, device="cuda").permute(0, 3, 1, 2)     # NHWC storage
+    y = torch.randint(0, 10, (8,), device="cuda")
+
+    def step(m):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = m(x).float()
+        loss = F.cross_entropy(logits, y)
+        loss.backward()
+        return loss.item(), logits.detach()
+
+    n0 = int(ops.launch_count())
+    l1, o1 = step(m1)
+    assert int(ops.launch_count()) - n0 >= 20 * 5        # every BN layer ran on our kernels
+    resnet_ops.ENABLE = False
+    try:
+        l2, o2 = step(m2)
+    finally:
+        resnet_ops.ENABLE = True
+    assert abs(l1 - l2) < 5e-2 * max(1.0, abs(l2))
+    g1 = torch.cat([p.grad.flatten() for p in m1.parameters()])
+    g2 = torch.cat([p.grad.flatten() for p in m2.parameters()])
+    cos = F.cosine_similarity(g1, g2, dim=0).item()
+    assert cos > 0.98, cos
+    for (n, b1), (_, b2) in zip(m1.named_buffers(), m2.named_buffers()):
+        if b1.dtype.is_floating_point:
+            assert torch.allclose(b1, b2, atol=2e-2, rtol=2e-2), n

@@ -12,9 +12,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = os.path.join(ROOT, "tests", "mp_allreduce_worker.py")
 
 
-def _run(nproc, backend, port, extra=()):
+FED_WORKER = os.path.join(ROOT, "tests", "mp_fedavg_worker.py")
+
+
+def _run(nproc, backend, port, extra=(), worker=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
-           "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER, "--backend", backend, *extra]
+           "--master-addr", "127.0.0.1", "--master-port", str(port), worker or WORKER, "--backend", backend, *extra]
     env = dict(os.environ, OMP_NUM_THREADS="2")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
@@ -35,3 +38,19 @@ def test_fused_allreduce_across_gpus(nproc):
         pytest.skip(f"needs {nproc} GPUs")
     rep = _run(nproc, "nccl", 29620 + nproc)
     assert rep["world"] == nproc and rep["checks"] >= 5 + 2 * 6
+
+
+def test_federated_round_gloo_world2():
+    """Whole product path on two CPU ranks: local training, CKKS encrypt, all-reduce, decrypt."""
+    rep = _run(2, "gloo", 29641, ["--rounds", "2"], worker=FED_WORKER)
+    assert rep["world"] == 2 and rep["max_abs_err"] < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.multigpu
+@pytest.mark.parametrize("nproc,model", [(2, "cnn2"), (2, "medcnn"), (8, "medcnn")])
+def test_federated_round_across_gpus(nproc, model):
+    if torch.cuda.device_count() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    rep = _run(nproc, "nccl", 29650 + nproc, ["--rounds", "2", "--model", model], worker=FED_WORKER)
+    assert rep["transport"] == "fused" and rep["max_abs_err"] < 1e-5

@@ -50,12 +50,27 @@ def main():
         with torch.autocast("cuda", dtype=torch.bfloat16):
             loss = F.cross_entropy(m(x).float(), y)
         loss.backward()
+    def graphed(enable):
+        resnet_ops.ENABLE = enable
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step()
+        t = timeit(lambda: g.replay(), iters=8)
+        resnet_ops.ENABLE = True
+        return t
     resnet_ops.ENABLE = True
     t_f = timeit(step, iters=5)
     resnet_ops.ENABLE = False
     t_a = timeit(step, iters=5)
     resnet_ops.ENABLE = True
-    res["resnet18_b32_224_fwd_bwd"] = {"fused_us": t_f, "aten_us": t_a, "speedup": t_a / t_f}
+    res["resnet18_b32_224_fwd_bwd_eager"] = {"fused_us": t_f, "aten_us": t_a, "speedup": t_a / t_f}
+    t_f, t_a = graphed(True), graphed(False)
+    res["resnet18_b32_224_fwd_bwd_cudagraph"] = {"fused_us": t_f, "aten_us": t_a, "speedup": t_a / t_f}
     for k, v in res.items():
         print(k, json.dumps(v))
     os.makedirs("gpurun_out", exist_ok=True)

@@ -3,7 +3,8 @@
 // [P = B*H*W pixels, C channels] bf16, statistics and parameters fp32.
 //
 //   forward : bn_stats (per-channel sum / sum-of-squares, one fp32 atomic per channel per CTA)
-//             bn_apply (normalise, scale/shift, + residual, ReLU; updates running statistics)
+//             bn_apply (finalises the statistics per CTA, normalise, scale/shift, + residual, ReLU; CTA 0
+//                       publishes mean / invstd and updates the running statistics)
 //   backward: bn_bwd_reduce (dbeta, dgamma with the ReLU mask recomputed from the output)
 //             bn_bwd_apply  (dx, and the gradient that flows into the residual branch)
 #include <cuda_bf16.h>
@@ -45,25 +46,32 @@ __global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __re
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], red[i]);
 }
 
-__global__ void bn_finalize_kernel(const float* __restrict__ sums, float* __restrict__ mean, float* __restrict__ invstd,
-                                   float* __restrict__ run_mean, float* __restrict__ run_var, int64_t P, int C,
-                                   float momentum, float eps) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float m = sums[c] / (float)P;
-  const float var = fmaxf(sums[C + c] / (float)P - m * m, 0.f);
-  mean[c] = m;
-  invstd[c] = rsqrtf(var + eps);
-  if (run_mean) {
-    run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * m;
-    run_var[c] = (1.f - momentum) * run_var[c] + momentum * var * ((float)P / (float)(P > 1 ? P - 1 : 1));
-  }
-}
-
+// Normalise + scale/shift (+ residual) (+ ReLU). Every CTA derives the per-channel scale/shift from the raw
+// sums into shared memory; CTA 0 also publishes mean / invstd (saved for backward) and the running statistics.
 __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
-                                const float* __restrict__ mean, const float* __restrict__ invstd,
-                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                __nv_bfloat16* __restrict__ y, int64_t P, int C, int relu) {
+                                const float* __restrict__ sums, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float* __restrict__ mean_out,
+                                float* __restrict__ invstd_out, float* __restrict__ run_mean,
+                                float* __restrict__ run_var, __nv_bfloat16* __restrict__ y, int64_t P, int C,
+                                float momentum, float eps, int relu) {
+  extern __shared__ float ss[];   // [C] scale, [C] shift
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float m = sums[c] / (float)P;
+    const float var = fmaxf(sums[C + c] / (float)P - m * m, 0.f);
+    const float is = rsqrtf(var + eps);
+    const float sc = gamma[c] * is;
+    ss[c] = sc;
+    ss[C + c] = beta[c] - m * sc;
+    if (blockIdx.x == 0) {
+      mean_out[c] = m;
+      invstd_out[c] = is;
+      if (run_mean) {
+        run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * m;
+        run_var[c] = (1.f - momentum) * run_var[c] + momentum * var * ((float)P / (float)(P > 1 ? P - 1 : 1));
+      }
+    }
+  }
+  __syncthreads();
   const int groups = C >> 3;
   const int64_t total = P * groups;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -82,7 +90,7 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int c = cg * 8 + 2 * i + j;
-        float z = (a[j] - mean[c]) * invstd[c] * gamma[c] + beta[c] + r[j];
+        float z = fmaf(a[j], ss[c], ss[C + c]) + r[j];
         if (relu) z = z > 0.f ? z : 0.f;
         a[j] = z;
       }
@@ -142,14 +150,24 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const
 }
 
 // dx = gamma*invstd * (dy' - dbeta/P - xhat*dgamma/P); dres = dy' (gradient into the residual branch).
+// Per channel: dx = a*dy' + b*x + c with a = gamma*invstd, b = -a*invstd*dgamma/P, c = -a*dbeta/P - b*mean.
 __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
                                     const float* __restrict__ sums, __nv_bfloat16* __restrict__ dx,
                                     __nv_bfloat16* __restrict__ dres, int64_t P, int C, int relu) {
+  extern __shared__ float ss[];   // [3][C]
+  const float invP = 1.f / (float)P;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float a = gamma[c] * invstd[c];
+    const float b = -a * invstd[c] * sums[C + c] * invP;
+    ss[c] = a;
+    ss[C + c] = b;
+    ss[2 * C + c] = -a * sums[c] * invP - b * mean[c];
+  }
+  __syncthreads();
   const int groups = C >> 3;
   const int64_t total = P * groups;
-  const float invP = 1.f / (float)P;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int cg = (int)(t % groups);
     const int64_t o = (t / groups) * C + cg * 8;
@@ -170,8 +188,7 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const 
         const uint32_t yb = j ? (yw[i] >> 16) : (yw[i] & 0xFFFFu);
         const bool on = !relu || (yb != 0u && (yb & 0x8000u) == 0u);
         const float dd = on ? d : 0.f;
-        const float xh = (xx - mean[c]) * invstd[c];
-        od[j] = gamma[c] * invstd[c] * (dd - sums[c] * invP - xh * sums[C + c] * invP);
+        od[j] = fmaf(ss[c], dd, fmaf(ss[C + c], xx, ss[2 * C + c]));
         rd[j] = dd;
       }
       const __nv_bfloat162 p0 = __floats2bfloat162_rn(od[0], od[1]);
@@ -198,11 +215,10 @@ void bn_forward(const void* x, const void* res, const float* gamma, const float*
   const int rows_per_iter = threads / (C / 8);
   bn_stats_kernel<<<blocks_for(P, rows_per_iter * 8, 148 * 4), threads, 2 * C * 4, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), sums, P, C);
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, mean, invstd, run_mean, run_var, P, C, momentum, eps);
-  bn_apply_kernel<<<blocks_for(P * (C / 8), 256, 148 * 16), 256, 0, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(res), mean, invstd, gamma, beta,
-      reinterpret_cast<__nv_bfloat16*>(y), P, C, relu);
-  hefl::cuda::note_launch(3);
+  bn_apply_kernel<<<blocks_for(P * (C / 8), 256 * 4, 148 * 8), 256, 2 * C * 4, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(res), sums, gamma, beta, mean,
+      invstd, run_mean, run_var, reinterpret_cast<__nv_bfloat16*>(y), P, C, momentum, eps, relu);
+  hefl::cuda::note_launch(2);
 }
 
 void bn_backward(const void* dy, const void* x, const void* y, const float* mean, const float* invstd,
@@ -213,7 +229,7 @@ void bn_backward(const void* dy, const void* x, const void* y, const float* mean
   bn_bwd_reduce_kernel<<<blocks_for(P, rows_per_iter * 8, 148 * 4), threads, 2 * C * 4, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x),
       reinterpret_cast<const __nv_bfloat16*>(y), mean, invstd, sums, P, C, relu);
-  bn_bwd_apply_kernel<<<blocks_for(P * (C / 8), 256, 148 * 16), 256, 0, st>>>(
+  bn_bwd_apply_kernel<<<blocks_for(P * (C / 8), 256 * 4, 148 * 8), 256, 3 * C * 4, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x),
       reinterpret_cast<const __nv_bfloat16*>(y), mean, invstd, gamma, sums, reinterpret_cast<__nv_bfloat16*>(dx),
       reinterpret_cast<__nv_bfloat16*>(dres), P, C, relu);

@@ -21,6 +21,11 @@ from .. import _ext
 ENABLE = True     # tests flip this to compare against the cuDNN/ATen path
 
 
+def _v(x: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """Zero-copy [B,H,W,C] view of a channels_last tensor (what the kernels index)."""
+    return None if x is None else x.permute(0, 2, 3, 1)
+
+
 def _nhwc(x: torch.Tensor) -> bool:
     return x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
 
@@ -33,7 +38,7 @@ class _BNActFn(torch.autograd.Function):
         y = torch.empty_like(x)                       # keeps channels_last strides
         stats = torch.empty(4 * C, dtype=torch.float32, device=x.device)
         mean, invstd, sums = stats[:C], stats[C:2 * C], stats[2 * C:]
-        ops.bn_forward(x, res, gamma, beta, run_mean, run_var, mean, invstd, sums, y, momentum, eps, relu)
+        ops.bn_forward(_v(x), _v(res), gamma, beta, run_mean, run_var, mean, invstd, sums, _v(y), momentum, eps, relu)
         ctx.save_for_backward(x, y, mean, invstd, gamma)
         ctx.relu = relu
         ctx.has_res = res is not None
@@ -49,7 +54,7 @@ class _BNActFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if ctx.has_res else None
         sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
-        ops.bn_backward(dy, x, y, mean, invstd, gamma, sums, dx, dres, ctx.relu)
+        ops.bn_backward(_v(dy), _v(x), _v(y), mean, invstd, gamma, sums, _v(dx), _v(dres), ctx.relu)
         return dx, dres, sums[C:], sums[:C], None, None, None, None, None
 
 
@@ -75,7 +80,7 @@ class _AvgPoolFn(torch.autograd.Function):
         ops = _ext.ops()
         B, C, H, W = x.shape
         out = torch.empty(B, C, dtype=torch.float32, device=x.device)
-        ops.avgpool_forward(x, out, B, H * W, C)
+        ops.avgpool_forward(_v(x), out, B, H * W, C)
         ctx.shape = (B, C, H, W)
         return out
 
@@ -84,7 +89,7 @@ class _AvgPoolFn(torch.autograd.Function):
         ops = _ext.ops()
         B, C, H, W = ctx.shape
         dx = torch.empty(B, C, H, W, dtype=torch.bfloat16, device=dout.device).contiguous(memory_format=torch.channels_last)
-        ops.avgpool_backward(dout.float().contiguous(), dx, B, H * W, C)
+        ops.avgpool_backward(dout.float().contiguous(), _v(dx), B, H * W, C)
         return dx
 
 

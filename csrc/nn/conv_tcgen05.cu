@@ -32,6 +32,7 @@
 #include "../he/kernels.h"
 #include "nn.h"
 #include "tc_common.cuh"
+#include "launch.cuh"
 
 namespace hefl {
 namespace nn {
@@ -189,15 +190,21 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: the set-up above and the weight tile (written only by the re-layout kernel, which never triggers its
+  // dependents early — launch.cuh) overlap the previous kernel's tail; activations only after the wait.
+  pdl_trigger();
+  if (warp == 8 && elect_one()) {
+    mbar_expect_tx(wfull, Cfg::W_BYTES);
+    for (int tap = 0; tap < 9; ++tap)
+      for (int kb = 0; kb < Cfg::NKB; ++kb)
+        tma_load_2d(sW + tap * Cfg::W_TAP + kb * Cfg::W_SUB, &tmW, kb * Cfg::KB,
+                    tap * a.co_total + blockIdx.y * CO, wfull);
+  }
+  pdl_wait();
 
   if (warp == 8) {
     // ===== TMA producer =====
     if (elect_one()) {
-      mbar_expect_tx(wfull, Cfg::W_BYTES);
-      for (int tap = 0; tap < 9; ++tap)
-        for (int kb = 0; kb < Cfg::NKB; ++kb)
-          tma_load_2d(sW + tap * Cfg::W_TAP + kb * Cfg::W_SUB, &tmW, kb * Cfg::KB,
-                      tap * a.co_total + blockIdx.y * CO, wfull);
       int buf = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
@@ -325,8 +332,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               const float o = __shfl_xor_sync(0xffffffffu, mine, 1);
               const bool rw = o > mine;
               const uint32_t id = rw ? (((pvbits >> (c + j)) & 1u) * 2u + 1u) : (((vbits >> (c + j)) & 1u) * 2u);
-              idx4[(c + j) >> 2] |= id << (((c + j) & 3) * 8);
               const float y = (rw ? o : mine) + bias8[c + j];
+              // bits 0-1: arg-max position (row*2 + col) in the window, bit 2: unit active (ReLU mask)
+              idx4[(c + j) >> 2] |= (id | (y > 0.f ? 4u : 0u)) << (((c + j) & 3) * 8);
               x[j] = y > 0.f ? y : 0.f;
             }
             packed[c >> 1] = pack_bf16x2(x[0], x[1]);
@@ -378,7 +386,7 @@ static void launch_tap_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Wt, Tap
   int gx = a.num_tiles < slots ? a.num_tiles : slots;
   if (gx < 1) gx = 1;
   dim3 grid(gx, ny);
-  kern<<<grid, 352, Cfg::SMEM, st>>>(tmA, tmW, a);
+  launch_pdl(kern, grid, dim3(352), Cfg::SMEM, st, tmA, tmW, a);
   hefl::cuda::note_launch();
 }
 
@@ -519,6 +527,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue();
   const int per_img = a.strips * a.rsplit;
 
   if (warp == 4) {
@@ -758,7 +767,7 @@ static void launch_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* DY, int B,
   if (gx > (FLAT ? a.nchunks : a.units)) gx = FLAT ? a.nchunks : a.units;
   if (gx < 1) gx = 1;
   dim3 grid(gx, cot);
-  kern<<<grid, 192, Cfg::SMEM, st>>>(tmX, tmD, a);
+  launch_pdl(kern, grid, dim3(192), Cfg::SMEM, st, tmX, tmD, a);
   hefl::cuda::note_launch();
 }
 

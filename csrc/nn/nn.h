@@ -25,6 +25,10 @@ void head_forward_backward(const void* feat, const float* W1, const float* b1, c
                            const float* W3, const float* b3, const int64_t* y, float* gW1, float* gb1, float* gW2,
                            float* gb2, float* gW3, float* gb3, void* dfeat, float* h1_buf, float* dh1_buf,
                            float* out, int64_t* step, int B, int F, int H1, int H2, int C, int train, cudaStream_t st);
+void set_pdl(int on);
+bool wgrad0_gather_supported(int W, int Wp, int CK, int Ci, int Co);
+void wgrad0_gather(const void* X, const void* g, const uint8_t* amax, float* dW, int B, int H, int W, int Hp, int Wp,
+                   cudaStream_t st);
 // ---- ResNet building blocks (resnet_kernels.cu) ----
 void bn_forward(const void* x, const void* res, const float* gamma, const float* beta, float* run_mean, float* run_var,
                 float* mean, float* invstd, float* sums, void* y, int64_t P, int C, float momentum, float eps, int relu,

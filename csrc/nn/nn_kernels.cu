@@ -5,14 +5,19 @@
 #include "../he/kernels.h"
 #include "../he/philox.h"
 #include "nn.h"
+#include "launch.cuh"
 
 namespace hefl {
 namespace nn {
+
+int g_pdl = 1;
+void set_pdl(int on) { g_pdl = on; }
 
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, int64_t n,
                             const int64_t* __restrict__ step, const float* __restrict__ lr_scale,
                             float lr, float decay, float beta1, float beta2, float eps) {
+  pdl_wait();   // parameter writer: no early trigger (see launch.cuh)
   const float t = (float)(*step);
   const float lr_t = lr * (lr_scale ? *lr_scale : 1.0f) / (1.0f + decay * (t - 1.0f));
   const float bc1 = 1.0f - powf(beta1, t);
@@ -38,7 +43,7 @@ void adam_step(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_
   if (n == 0) return;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n,
+  launch_pdl(adam_kernel, dim3(blocks), dim3(256), 0, st, p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n,
                                       step, lr_scale, lr, decay, beta1, beta2, eps);
   hefl::cuda::note_launch();
 }
@@ -58,6 +63,7 @@ namespace nn {
 __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ x, const float* __restrict__ theta,
                                      __nv_bfloat16* __restrict__ X, int B, int H, int W, uint64_t aug_seed,
                                      const int64_t* __restrict__ step) {
+  pdl_prologue();
   const int b = blockIdx.y;
   const int HW = H * W;
   float tl[6];
@@ -119,7 +125,7 @@ void preprocess_u8(const uint8_t* x, const float* theta, void* X, int B, int H, 
   int bx = (H * W + 255) / 256;
   if (bx > 64) bx = 64;
   dim3 grid(bx, B);
-  preprocess_u8_kernel<<<grid, 256, 0, st>>>(x, theta, reinterpret_cast<__nv_bfloat16*>(X), B, H, W, aug_seed, step);
+  launch_pdl(preprocess_u8_kernel, dim3(grid), dim3(256), 0, st, x, theta, reinterpret_cast<__nv_bfloat16*>(X), B, H, W, aug_seed, step);
   hefl::cuda::note_launch();
 }
 
@@ -129,6 +135,7 @@ void preprocess_u8(const uint8_t* x, const float* theta, void* X, int B, int H, 
 __global__ void unpool_relu_kernel(const __nv_bfloat16* __restrict__ g, const uint8_t* __restrict__ amax,
                                    const __nv_bfloat16* __restrict__ ypool, __nv_bfloat16* __restrict__ dY, int B,
                                    int H, int W, int Hp, int Wp, int Co) {
+  pdl_prologue();
   // One thread = one 2x2 window x 8 channels: reads the pooled data once, writes all four
   // positions (windows outside the pooled grid write zeros so the whole H x W grid is defined).
   const int groups = Co >> 3;
@@ -181,7 +188,7 @@ void unpool_relu(const void* g, const uint8_t* amax, const void* ypool, void* dY
                  int Wp, int Co, cudaStream_t st) {
   const int per_row = ((W + 1) / 2) * (Co / 8);
   dim3 grid((per_row + 127) / 128, B * ((H + 1) / 2));
-  unpool_relu_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), amax,
+  launch_pdl(unpool_relu_kernel, dim3(grid), dim3(128), 0, st, reinterpret_cast<const __nv_bfloat16*>(g), amax,
                                            reinterpret_cast<const __nv_bfloat16*>(ypool),
                                            reinterpret_cast<__nv_bfloat16*>(dY), B, H, W, Hp, Wp, Co);
   hefl::cuda::note_launch();
@@ -191,6 +198,7 @@ void unpool_relu(const void* g, const uint8_t* amax, const void* ypool, void* dY
 // operand, channel-padded) and Wd [tap][Ci][Co] (dgrad B operand).
 __global__ void conv_weight_relayout_kernel(const __nv_bfloat16* __restrict__ shadow, const ConvLayerTable t,
                                             __nv_bfloat16* __restrict__ Wf, __nv_bfloat16* __restrict__ Wd) {
+  pdl_wait();   // parameter writer: no early trigger (see launch.cuh)
   const int l = blockIdx.y;
   const int Ci = t.Ci[l], CK = t.CK[l], Co = t.Co[l];
   const __nv_bfloat16* w = shadow + t.w_off[l];
@@ -210,7 +218,7 @@ __global__ void conv_weight_relayout_kernel(const __nv_bfloat16* __restrict__ sh
 
 void conv_weight_relayout(const void* shadow, const ConvLayerTable& t, void* Wf, void* Wd, cudaStream_t st) {
   dim3 grid(32, t.n);
-  conv_weight_relayout_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(shadow), t,
+  launch_pdl(conv_weight_relayout_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(shadow), t,
                                                     reinterpret_cast<__nv_bfloat16*>(Wf),
                                                     reinterpret_cast<__nv_bfloat16*>(Wd));
   hefl::cuda::note_launch();
@@ -220,6 +228,7 @@ void conv_weight_relayout(const void* shadow, const ConvLayerTable& t, void* Wf,
 // parameter layout ([Co][Ci][3][3], then bias); clears dW32 for the next step.
 __global__ void conv_grad_finalize_kernel(float* __restrict__ dW32, const ConvLayerTable t,
                                           float* __restrict__ grad) {
+  pdl_prologue();
   const int l = blockIdx.y;
   const int Ci = t.Ci[l], CK = t.CK[l], Co = t.Co[l];
   float* src = dW32 + t.dw_off[l];
@@ -232,15 +241,16 @@ __global__ void conv_grad_finalize_kernel(float* __restrict__ dW32, const ConvLa
     grad[t.b_off[l] + i] = src[(size_t)9 * CK * Co + i];
 }
 __global__ void zero_f32_kernel(float* __restrict__ p, int64_t n) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0.f;
 }
 
 void conv_grad_finalize(float* dW32, const ConvLayerTable& t, float* grad, cudaStream_t st) {
   dim3 grid(32, t.n);
-  conv_grad_finalize_kernel<<<grid, 256, 0, st>>>(dW32, t, grad);
+  launch_pdl(conv_grad_finalize_kernel, dim3(grid), dim3(256), 0, st, dW32, t, grad);
   const int l = t.n - 1;
   const int64_t total = t.dw_off[l] + (int64_t)(9 * t.CK[l] + 1) * t.Co[l];
-  zero_f32_kernel<<<64, 256, 0, st>>>(dW32, total);
+  launch_pdl(zero_f32_kernel, dim3(64), dim3(256), 0, st, dW32, total);
   hefl::cuda::note_launch(2);
 }
 
@@ -272,6 +282,7 @@ __global__ void fused_update_kernel(float* __restrict__ dW32, const ConvLayerTab
                                     __nv_bfloat16* __restrict__ Wd, const int64_t* __restrict__ step,
                                     const float* __restrict__ lr_scale, AdamHyper h, int64_t dense_off,
                                     int64_t n_trainable) {
+  pdl_wait();   // parameter writer: no early trigger (see launch.cuh)
   const float tt = (float)(*step);
   const float lr_t = h.lr * (lr_scale ? *lr_scale : 1.f) / (1.f + h.decay * (tt - 1.f));
   const float alpha = lr_t * sqrtf(1.f - powf(h.beta2, tt)) / (1.f - powf(h.beta1, tt));
@@ -321,7 +332,7 @@ void fused_update(float* dW32, const ConvLayerTable& t, float* flat, float* grad
                   float beta2, float eps, int64_t dense_off, int64_t n_trainable, cudaStream_t st) {
   dim3 grid(48, t.n + 1);
   AdamHyper h{lr, decay, beta1, beta2, eps};
-  fused_update_kernel<<<grid, 256, 0, st>>>(dW32, t, flat, grad, m, v, reinterpret_cast<__nv_bfloat16*>(shadow),
+  launch_pdl(fused_update_kernel, dim3(grid), dim3(256), 0, st, dW32, t, flat, grad, m, v, reinterpret_cast<__nv_bfloat16*>(shadow),
                                             reinterpret_cast<__nv_bfloat16*>(Wf), reinterpret_cast<__nv_bfloat16*>(Wd),
                                             step, lr_scale, h, dense_off, n_trainable);
   hefl::cuda::note_launch();
@@ -348,6 +359,7 @@ namespace nn {
 __global__ void __launch_bounds__(128)
 head_fc1_fwd_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict__ W1,
                     const float* __restrict__ b1, float* __restrict__ h1, int B, int F, int H1) {
+  pdl_trigger();
   extern __shared__ float sm1[];
   const int FP = F + 1;
   float* fs = sm1;                 // [B][F+1]
@@ -355,6 +367,16 @@ head_fc1_fwd_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restr
   const int j0 = blockIdx.x * 4;
   const int F8 = F >> 3, F4 = F >> 2;
   const uint4* src = reinterpret_cast<const uint4*>(feat);
+  // weights first: they do not depend on the previous kernel, so this overlaps its tail (PDL)
+#pragma unroll 4
+  for (int i = threadIdx.x; i < 4 * F4; i += blockDim.x) {
+    const int jj = i / F4, k4 = i - jj * F4;
+    const float4 v = (j0 + jj) < H1 ? reinterpret_cast<const float4*>(W1 + (size_t)(j0 + jj) * F)[k4]
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    float* dst = ws + jj * FP + k4 * 4;
+    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+  }
+  pdl_wait();
 #pragma unroll 8
   for (int i = threadIdx.x; i < B * F8; i += blockDim.x) {   // B*F/8 16-byte loads, 8+ in flight per thread
     const uint4 v = src[i];
@@ -366,14 +388,6 @@ head_fc1_fwd_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restr
       dst[2 * q] = __uint_as_float(w[q] << 16);
       dst[2 * q + 1] = __uint_as_float(w[q] & 0xFFFF0000u);
     }
-  }
-#pragma unroll 4
-  for (int i = threadIdx.x; i < 4 * F4; i += blockDim.x) {
-    const int jj = i / F4, k4 = i - jj * F4;
-    const float4 v = (j0 + jj) < H1 ? reinterpret_cast<const float4*>(W1 + (size_t)(j0 + jj) * F)[k4]
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-    float* dst = ws + jj * FP + k4 * 4;
-    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
   }
   __syncthreads();
   const int b = threadIdx.x >> 2, jj = threadIdx.x & 3;
@@ -409,6 +423,7 @@ struct HeadMidArgs {
 // k2: fc2 (each thread: 2 samples x 4 neurons, operands reused from registers), fc3, loss, dW3, dh2.
 __global__ void __launch_bounds__(256)
 head_mid_kernel(const HeadMidArgs a) {
+  pdl_trigger();
   extern __shared__ float sm[];
   const int B = a.B, H1 = a.H1, H2 = a.H2, C = a.C;
   float* h1 = sm;                       // [B][H1+1]
@@ -419,12 +434,6 @@ head_mid_kernel(const HeadMidArgs a) {
   float* W3 = red + 2 * B;              // [C][H2]
   const int tid = threadIdx.x, nt = blockDim.x;
   const int H14 = H1 >> 2;
-#pragma unroll 4
-  for (int i = tid; i < B * H14; i += nt) {
-    const float4 v = reinterpret_cast<const float4*>(a.h1)[i];
-    float* d = h1 + (i / H14) * (H1 + 1) + (i % H14) * 4;
-    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-  }
 #pragma unroll 8
   for (int i = tid; i < H2 * H14; i += nt) {
     const float4 v = reinterpret_cast<const float4*>(a.W2)[i];
@@ -432,6 +441,13 @@ head_mid_kernel(const HeadMidArgs a) {
     d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
   }
   for (int i = tid; i < C * H2; i += nt) W3[i] = a.W3[i];
+  pdl_wait();          // weights staged above overlap the previous kernel; activations only from here
+#pragma unroll 4
+  for (int i = tid; i < B * H14; i += nt) {
+    const float4 v = reinterpret_cast<const float4*>(a.h1)[i];
+    float* d = h1 + (i / H14) * (H1 + 1) + (i % H14) * 4;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
   __syncthreads();
   {  // fc2: tiles of 2 samples x 4 neurons
     const int tiles_j = H2 >> 2, tiles = (B >> 1) * tiles_j;
@@ -523,6 +539,7 @@ head_mid_kernel(const HeadMidArgs a) {
 __global__ void __launch_bounds__(256)
 head_fc2_bwd_kernel(const float* __restrict__ dh2g, const float* __restrict__ h1g, const float* __restrict__ W2,
                     float* __restrict__ gW2, float* __restrict__ gb2, float* __restrict__ dh1, int B, int H1, int H2) {
+  pdl_trigger();
   extern __shared__ float sm[];
   float* d = sm;                       // [B][H2+1]
   float* hs = d + B * (H2 + 1);        // [B][16]
@@ -530,11 +547,12 @@ head_fc2_bwd_kernel(const float* __restrict__ dh2g, const float* __restrict__ h1
   const int tid = threadIdx.x, nt = blockDim.x;
   const int i0 = blockIdx.x * 16;
 #pragma unroll 4
+  for (int i = tid; i < H2 * 16; i += nt) ws[(i >> 4) * 17 + (i & 15)] = (i0 + (i & 15)) < H1 ? W2[(size_t)(i >> 4) * H1 + i0 + (i & 15)] : 0.f;
+  pdl_wait();
+#pragma unroll 4
   for (int i = tid; i < B * H2; i += nt) d[(i / H2) * (H2 + 1) + i % H2] = dh2g[i];
 #pragma unroll 2
   for (int i = tid; i < B * 16; i += nt) hs[i] = (i0 + (i & 15)) < H1 ? h1g[(i >> 4) * H1 + i0 + (i & 15)] : 0.f;
-#pragma unroll 4
-  for (int i = tid; i < H2 * 16; i += nt) ws[(i >> 4) * 17 + (i & 15)] = (i0 + (i & 15)) < H1 ? W2[(size_t)(i >> 4) * H1 + i0 + (i & 15)] : 0.f;
   __syncthreads();
   for (int o = tid; o < H2 * 16; o += nt) {                    // dW2[j][i0+k]
     const int j = o >> 4, k = o & 15;
@@ -573,6 +591,7 @@ __global__ void __launch_bounds__(256)
 head_fc1_bwd_kernel(const float* __restrict__ dh1, const __nv_bfloat16* __restrict__ feat,
                     const float* __restrict__ W1, float* __restrict__ gW1, float* __restrict__ gb1,
                     __nv_bfloat16* __restrict__ dfeat, int B, int F, int H1) {
+  pdl_trigger();
   extern __shared__ float sm[];
   float* d = sm;                       // [B][H1+1]
   float* fs = d + B * (H1 + 1);        // [B][16]
@@ -580,16 +599,17 @@ head_fc1_bwd_kernel(const float* __restrict__ dh1, const __nv_bfloat16* __restri
   const int tid = threadIdx.x, nt = blockDim.x;
   const int k0 = blockIdx.x * 16;
 #pragma unroll 8
+  for (int i = tid; i < H1 * 16; i += nt) {
+    const int j = i >> 4, k = i & 15;
+    ws[j * 17 + k] = k0 + k < F ? W1[(size_t)j * F + k0 + k] : 0.f;
+  }
+  pdl_wait();
+#pragma unroll 8
   for (int i = tid; i < B * H1; i += nt) d[(i / H1) * (H1 + 1) + i % H1] = dh1[i];
 #pragma unroll 2
   for (int i = tid; i < B * 16; i += nt) {
     const int b = i >> 4, k = i & 15;
     fs[i] = k0 + k < F ? __bfloat162float(feat[b * F + k0 + k]) : 0.f;
-  }
-#pragma unroll 8
-  for (int i = tid; i < H1 * 16; i += nt) {
-    const int j = i >> 4, k = i & 15;
-    ws[j * 17 + k] = k0 + k < F ? W1[(size_t)j * F + k0 + k] : 0.f;
   }
   __syncthreads();
   for (int o = tid; o < H1 * 16; o += nt) {
@@ -631,18 +651,18 @@ void head_forward_backward(const void* feat, const float* W1, const float* b1, c
   float* dh2_buf = dh1_buf + (size_t)B * H1;                  // scratch tail: [B][H2]
   const int smem_a = (B + 4) * (F + 1) * 4;
   cudaFuncSetAttribute(head_fc1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
-  head_fc1_fwd_kernel<<<(H1 + 3) / 4, 128, smem_a, st>>>(f, W1, b1, h1_buf, B, F, H1);
+  launch_pdl(head_fc1_fwd_kernel, dim3((H1 + 3) / 4), dim3(128), smem_a, st, f, W1, b1, h1_buf, B, F, H1);
   HeadMidArgs a{h1_buf, W2, b2, W3, b3, y, gW3, gb3, dh2_buf, out, step, B, H1, H2, C, train};
   const int smem_b = (B * (H1 + 1) + H2 * (H1 + 1) + B * (H2 + 1) + B * C + 2 * B + C * H2) * 4;
   cudaFuncSetAttribute(head_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
-  head_mid_kernel<<<1, 256, smem_b, st>>>(a);
+  launch_pdl(head_mid_kernel, dim3(1), dim3(256), smem_b, st, a);
   hefl::cuda::note_launch(2);
   if (train) {
     const int smem_c = (B * (H2 + 1) + B * 16 + H2 * 17) * 4;
-    head_fc2_bwd_kernel<<<(H1 + 15) / 16, 256, smem_c, st>>>(dh2_buf, h1_buf, W2, gW2, gb2, dh1_buf, B, H1, H2);
+    launch_pdl(head_fc2_bwd_kernel, dim3((H1 + 15) / 16), dim3(256), smem_c, st, dh2_buf, h1_buf, W2, gW2, gb2, dh1_buf, B, H1, H2);
     const int smem_d = (B * (H1 + 1) + B * 16 + H1 * 17) * 4;
     cudaFuncSetAttribute(head_fc1_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_d);
-    head_fc1_bwd_kernel<<<(F + 15) / 16, 256, smem_d, st>>>(dh1_buf, f, W1, gW1, gb1,
+    launch_pdl(head_fc1_bwd_kernel, dim3((F + 15) / 16), dim3(256), smem_d, st, dh1_buf, f, W1, gW1, gb1,
                                                             reinterpret_cast<__nv_bfloat16*>(dfeat), B, F, H1);
     hefl::cuda::note_launch(2);
   }

@@ -42,6 +42,7 @@ CUDA_SOURCES = [
     "nn/conv_tcgen05.cu",
     "nn/nn_kernels.cu",
     "nn/resnet_kernels.cu",
+    "nn/wgrad_gather.cu",
 ]
 HOST_SOURCES = [
     "he/host_math.cpp",

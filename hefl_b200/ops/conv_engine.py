@@ -15,6 +15,8 @@ All buffers are allocated once; the whole step is CUDA-graph capturable.
 """
 from __future__ import annotations
 
+import os
+
 import math
 from typing import List, Optional
 
@@ -35,6 +37,7 @@ class MedCNNEngine:
         if device.type != "cuda":
             raise RuntimeError("the tcgen05 engine needs a CUDA device (sm_100a)")
         self.ops = _ext.ops()
+        self.ops.set_pdl(0 if os.environ.get("HEFL_PDL", "1") == "0" else 1)   # programmatic dependent launch
         self.model, self.pack, self.cfg, self.device = model, pack, cfg, device
         B, S = cfg.batch_size, cfg.image_size
         if cfg.in_channels != 3:
@@ -61,6 +64,9 @@ class MedCNNEngine:
             self.Co.append(co)
             h = (h - 2) // 2
         self.H.append(h)                 # feature map side
+        # layer-1 weight gradient by gather from the pooled gradient (csrc/nn/wgrad_gather.cu)
+        self.gather_wgrad0 = (os.environ.get("HEFL_GATHER_WGRAD0", "1") != "0" and self.Co[0] == 32
+                              and self.CK[0] == 16 and self.H[0] <= 256)
         bf = dict(dtype=torch.bfloat16, device=device)
         self.P = [B * self.H[l] * self.H[l] for l in range(self.n + 1)]
         # activations / gradients (all NHWC bf16 viewed as [pixels, channels])
@@ -72,7 +78,8 @@ class MedCNNEngine:
             hp = self.H[l + 1]
             self.X.append(torch.zeros(B * hp * hp, self.Co[l], **bf))
             self.amax.append(torch.zeros(B * hp * hp, self.Co[l], dtype=torch.uint8, device=device))
-            self.dY.append(torch.zeros(self.P[l], self.Co[l], **bf))
+            # layer 1 normally takes the gather path (no conv-grid gradient at all): allocate lazily
+            self.dY.append(None if l == 0 else torch.zeros(self.P[l], self.Co[l], **bf))
             self.gX.append(torch.zeros(B * hp * hp, self.Co[l], **bf))
         # weights
         wf_off, wd_off, dw_off = [0], [0], [0]
@@ -186,6 +193,12 @@ class MedCNNEngine:
         main = torch.cuda.current_stream(self.device)
         for l in range(self.n - 1, -1, -1):
             h = self.H[l]
+            if l == 0 and self.gather_wgrad0:
+                # 3-channel layer: weight gradient gathered straight from the pooled gradient
+                self.ops.wgrad0_gather(self._x0_base, g, self.amax[0], self._dw(0), self.B, h, h)
+                break
+            if self.dY[l] is None:
+                self.dY[l] = torch.zeros(self.P[l], self.Co[l], dtype=torch.bfloat16, device=self.device)
             self.ops.unpool_relu(g, self.amax[l], self.X[l + 1], self.dY[l], self.B, h, h, self.Co[l])
             if self.two_streams and l > 0:
                 # wgrad(l) only needs X[l] and dY[l]; dgrad(l) -> unpool(l-1) -> ... proceeds meanwhile

@@ -50,7 +50,7 @@ def test_conv_fwd_pool_matches_torch(B, H, Ci, CK, Co):
     Wo = H - 2
     ih, iw = idx // Wo, idx % Wo
     pos_ref = (ih % 2) * 2 + (iw % 2)
-    pos_got = am.view(B, Hp, Hp, Co).permute(0, 3, 1, 2).long()
+    pos_got = (am & 3).view(B, Hp, Hp, Co).permute(0, 3, 1, 2).long()   # bit 2 = ReLU-active flag
     sel = ref > 0.05
     agree = (pos_ref[sel] == pos_got[sel]).float().mean()
     assert agree > 0.995
@@ -135,7 +135,43 @@ def test_preprocess_matches_grid_sample():
     assert (X.view(B, H, H, 16)[..., :3].float() - ref).abs().max() < 1e-2
 
 
-def test_engine_gradients_match_autograd():
+@pytest.mark.parametrize("H", [256, 66])
+def test_wgrad0_gather_matches_autograd(H):
+    """Layer-1 weight/bias gradient gathered from the pooled gradient == autograd through
+    conv -> ReLU -> max-pool, with arg-max/active bits produced by the forward kernel itself."""
+    B, Ci, Co = 4, 3, 32
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = _bf(torch.rand(B, Ci, H, H, device="cuda", generator=g))
+    w = _bf(torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) * 0.3).float().requires_grad_(True)
+    bias = (torch.randn(Co, device="cuda", generator=g) * 0.1).requires_grad_(True)
+    Hp = (H - 2) // 2
+    P = B * H * H
+    X = torch.zeros(P + 8, 16, dtype=torch.bfloat16, device="cuda")
+    X[:P, :Ci] = x.permute(0, 2, 3, 1).reshape(P, Ci)
+    Wf = torch.zeros(9, Co, 16, dtype=torch.bfloat16, device="cuda")
+    Wf[:, :, :Ci] = w.detach().permute(2, 3, 0, 1).reshape(9, Co, Ci).to(torch.bfloat16)
+    out = torch.zeros(B * Hp * Hp, Co, dtype=torch.bfloat16, device="cuda")
+    amax = torch.zeros(B * Hp * Hp, Co, dtype=torch.uint8, device="cuda")
+    ops.conv_fwd_pool(X[:P], Wf.view(-1), bias.detach(), out, amax, B, H, H, 16, Co)
+    pooled = F.max_pool2d(F.relu(F.conv2d(x.float(), w, bias)), 2)
+    # the forward kernel's own mask decides which units are active; use its pooled output for the
+    # reference mask so ties at exactly zero cannot differ
+    act = (amax.view(B, Hp, Hp, Co) & 4) != 0
+    assert torch.equal(act, out.view(B, Hp, Hp, Co) > 0)
+    gp = _bf(torch.randn(B, Co, Hp, Hp, device="cuda", generator=g))
+    pooled.backward(gp.float())
+    dW32 = torch.zeros(9 * 16 + 1, Co, dtype=torch.float32, device="cuda")
+    ops.wgrad0_gather(X, gp.permute(0, 2, 3, 1).contiguous().view(-1, Co), amax, dW32.view(-1), B, H, H)
+    torch.cuda.synchronize()
+    got_w = dW32[:144].view(9, 16, Co)[:, :Ci, :].permute(2, 1, 0).reshape(Co, Ci, 3, 3)
+    assert float(dW32[:144].view(9, 16, Co)[:, Ci:, :].abs().max()) == 0.0
+    ref_w, ref_b = w.grad, bias.grad
+    assert (got_w - ref_w).abs().max() <= 2e-3 * ref_w.abs().max() + 1e-3
+    assert (dW32[144] - ref_b).abs().max() <= 2e-3 * ref_b.abs().max() + 1e-3
+
+
+@pytest.mark.parametrize("gather", [True, False])
+def test_engine_gradients_match_autograd(gather):
     """Whole medical CNN: engine forward/backward vs PyTorch autograd on the same weights."""
     from hefl_b200.config import FLConfig
     from hefl_b200.models import ParamPack, create_model
@@ -150,6 +186,7 @@ def test_engine_gradients_match_autograd():
     pack.flat.copy_(pack.flat.to(torch.bfloat16).float())
     eng = MedCNNEngine(model, pack, cfg, dev)
     eng.fused_step = False          # keep the gradients in pack.grad (the fused update consumes them in place)
+    eng.gather_wgrad0 = gather      # layer-1 weight gradient: gather kernel vs unpool + tensor-core wgrad
     g = torch.Generator(device="cuda").manual_seed(7)
     x = torch.randint(0, 256, (8, 256, 256, 3), dtype=torch.uint8, device="cuda", generator=g)
     y = torch.randint(0, 2, (8,), device="cuda", generator=g)

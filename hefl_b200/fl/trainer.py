@@ -71,6 +71,13 @@ class LocalTrainer:
 
             self.engine = MedCNNEngine(model, pack, cfg, device)
             self.engine.step_ref = self.step_t
+            # staged input pipeline: batch i+1 is pre-processed into the other X0 slot on `prep_stream`
+            # while the graph of step i runs; one captured graph per (train/eval, slot)
+            self.static_y2 = [torch.zeros(B, dtype=torch.int64, device=device) for _ in range(2)]
+            self._graphs: Dict[Tuple[bool, int], torch.cuda.CUDAGraph] = {}
+            self.prep_stream = torch.cuda.Stream(device)
+            self._slot_ready = [torch.cuda.Event() for _ in range(2)]
+            self._slot_free = [torch.cuda.Event() for _ in range(2)]
 
     # ------------------------------------------------------------------ one step (eager)
     def _prep(self, x_u8: torch.Tensor, train: bool) -> torch.Tensor:
@@ -95,6 +102,14 @@ class LocalTrainer:
             loss.backward()
             self.out_train[0] = loss.detach()
             self.out_train[1] = (logits.argmax(1) == y).sum()
+        self._optimizer_step()
+
+    def _train_staged(self, slot: int) -> None:
+        """Graph body of the tcgen05 engine: forward/backward on the pre-processed batch of ``slot`` + update."""
+        self.engine.train_step_staged(slot, self.static_y2[slot], self.out_train)
+        self._optimizer_step()
+
+    def _optimizer_step(self) -> None:
         c = self.cfg
         if self.engine is not None and self.engine.fused_step:
             self.engine.fused_update(self.m, self.v, self.step_t, self.lr_scale, c)   # step counter bumped by the head kernel
@@ -121,21 +136,47 @@ class LocalTrainer:
         snap = (self.pack.flat.clone(), self.m.clone(), self.v.clone(), self.step_t.clone())
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
+        eng = self.engine
         with torch.cuda.stream(side):
+            if eng is not None:
+                for slot in range(2):
+                    eng.preprocess(self.static_x, slot, False, False)
             for _ in range(3):
-                self._train_eager(self.static_x, self.static_y)
-                self._eval_eager(self.static_x, self.static_y)
+                if eng is not None:
+                    for slot in range(2):
+                        self._train_staged(slot)
+                        eng.eval_step_staged(slot, self.static_y2[slot], self.out_eval)
+                else:
+                    self._train_eager(self.static_x, self.static_y)
+                    self._eval_eager(self.static_x, self.static_y)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         l0 = int(self.ops.launch_count())
-        self._graph_train = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph_train):
-            self._train_eager(self.static_x, self.static_y)
-        l1 = int(self.ops.launch_count())
-        self._graph_eval = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph_eval):
-            self._eval_eager(self.static_x, self.static_y)
-        self.graph_launches = [l1 - l0, int(self.ops.launch_count()) - l1]
+        if eng is not None:
+            counts = {}
+            for slot in range(2):
+                for train in (True, False):
+                    a = int(self.ops.launch_count())
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        if train:
+                            self._train_staged(slot)
+                        else:
+                            with torch.no_grad():
+                                eng.eval_step_staged(slot, self.static_y2[slot], self.out_eval)
+                    self._graphs[(train, slot)] = g
+                    counts[(train, slot)] = int(self.ops.launch_count()) - a
+            self._graph_train, self._graph_eval = self._graphs[(True, 0)], self._graphs[(False, 0)]
+            self.graph_launches = [counts[(True, 0)] + 1, counts[(False, 0)] + 1]     # + the pre-process launch
+        else:
+            self._graph_train = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_train):
+                self._train_eager(self.static_x, self.static_y)
+            l1 = int(self.ops.launch_count())
+            self._graph_eval = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_eval):
+                self._eval_eager(self.static_x, self.static_y)
+            self.graph_launches = [l1 - l0, int(self.ops.launch_count()) - l1]
         # undo the warm-up updates
         self.pack.flat.copy_(snap[0]); self.m.copy_(snap[1]); self.v.copy_(snap[2]); self.step_t.copy_(snap[3])
         self.pack.grad.zero_()
@@ -149,8 +190,12 @@ class LocalTrainer:
         if self.use_graph:
             if self._graph_train is None:
                 self._capture()
-            self.static_x.copy_(x_u8, non_blocking=True)
-            self.static_y.copy_(y, non_blocking=True)
+            if self.engine is not None:
+                self.engine.preprocess(x_u8, 0, True, self.augment)     # straight into X0[0], no staging copy
+                self.static_y2[0].copy_(y, non_blocking=True)
+            else:
+                self.static_x.copy_(x_u8, non_blocking=True)
+                self.static_y.copy_(y, non_blocking=True)
             self._graph_train.replay()
             self.replayed_launches += self.graph_launches[0]
         else:
@@ -161,13 +206,61 @@ class LocalTrainer:
         if self.use_graph:
             if self._graph_eval is None:
                 self._capture()
-            self.static_x.copy_(x_u8, non_blocking=True)
-            self.static_y.copy_(y, non_blocking=True)
+            if self.engine is not None:
+                self.engine.preprocess(x_u8, 0, False, False)
+                self.static_y2[0].copy_(y, non_blocking=True)
+            else:
+                self.static_x.copy_(x_u8, non_blocking=True)
+                self.static_y.copy_(y, non_blocking=True)
             self._graph_eval.replay()
             self.replayed_launches += self.graph_launches[1]
         else:
             self._eval_eager(x_u8, y)
         return self.out_eval
+
+    def _run_epoch(self, feeder, train: bool, stats: torch.Tensor) -> None:
+        """One pass over ``feeder``; per-step [loss, ncorrect] land in ``stats`` (pinned host rows).
+
+        tcgen05 engine + CUDA graphs: software pipeline over batches — batch i+1 is fetched (H2D or
+        on-device gather) and pre-processed into the other X0 slot on ``prep_stream`` while the captured
+        graph of step i runs on the main stream; events hand the slots back and forth."""
+        if self.engine is None or not self.use_graph:
+            for i, (x, y) in enumerate(feeder.epoch()):
+                out = self.train_step(x, y) if train else self.eval_step(x, y)
+                stats[i].copy_(out, non_blocking=True)       # D2H of the step's loss/accuracy
+            return
+        if not self._graphs:
+            self._capture()
+        main, prep = torch.cuda.current_stream(self.device), self.prep_stream
+        prep.wait_stream(main)
+        for ev in self._slot_free:
+            ev.record(main)
+        it = iter(feeder.epoch())
+        n = feeder.steps
+        out = self.out_train if train else self.out_eval
+
+        def stage(slot: int) -> None:
+            with torch.cuda.stream(prep):
+                prep.wait_event(self._slot_free[slot])        # the graph that last read this slot is done
+                x, y = next(it)                               # feeder work (gather / wait for H2D) on prep
+                self.engine.preprocess(x, slot, train, self.augment and train)
+                self.static_y2[slot].copy_(y, non_blocking=True)
+                self._slot_ready[slot].record(prep)
+
+        stage(0)
+        for i in range(n):
+            slot = i & 1
+            if i + 1 < n:
+                stage(slot ^ 1)
+            main.wait_event(self._slot_ready[slot])
+            self._graphs[(train, slot)].replay()
+            self._slot_free[slot].record(main)
+            stats[i].copy_(out, non_blocking=True)
+        self.replayed_launches += n * self.graph_launches[0 if train else 1]
+        with torch.cuda.stream(prep):
+            for _ in it:                                      # let the feeder finish its bookkeeping
+                pass
+        main.wait_stream(prep)
 
     def fit(self, train: BatchFeeder, val: Optional[BatchFeeder], epochs: int,
             early_stopping: Optional[int] = 5, restore_best: bool = True,
@@ -186,16 +279,12 @@ class LocalTrainer:
         for ep in range(epochs):
             self.model.train()
             ts = ts_all[: train.steps]
-            for i, (x, y) in enumerate(train.epoch()):
-                out = self.train_step(x, y)
-                ts[i].copy_(out, non_blocking=True)       # D2H of the step's loss/accuracy
+            self._run_epoch(train, True, ts)
             vs = None
             if val is not None and val.steps > 0:
                 self.model.eval()
                 vs = vs_all[:nval]
-                for i, (x, y) in enumerate(val.epoch()):
-                    out = self.eval_step(x, y)
-                    vs[i].copy_(out, non_blocking=True)
+                self._run_epoch(val, False, vs)
             if self.cuda:
                 torch.cuda.current_stream(self.device).synchronize()
             loss = float(ts[:, 0].mean())
@@ -245,7 +334,12 @@ class LocalTrainer:
         self.pack.grad.zero_()
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
-        return {"m": self.m.cpu(), "v": self.v.cpu(), "step": self.step_t.cpu(), "lr_scale": self.lr_scale.cpu()}
+        sd = {"m": self.m.cpu(), "v": self.v.cpu(), "step": self.step_t.cpu(), "lr_scale": self.lr_scale.cpu()}
+        if self.engine is not None:
+            sd["prep_count"] = torch.tensor(self.engine.prep_count, dtype=torch.int64)   # augmentation stream position
+        return sd
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
         self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.step_t.copy_(sd["step"]); self.lr_scale.copy_(sd["lr_scale"])
+        if self.engine is not None and "prep_count" in sd:
+            self.engine.prep_count = int(sd["prep_count"])

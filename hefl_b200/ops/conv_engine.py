@@ -71,8 +71,11 @@ class MedCNNEngine:
         self.P = [B * self.H[l] * self.H[l] for l in range(self.n + 1)]
         # activations / gradients (all NHWC bf16 viewed as [pixels, channels])
         # layer-1 input with 8 pixels of slack: its wgrad reads 4-pixel windows (overlapping TMA rows)
-        self._x0_base = torch.zeros(self.P[0] + 8, 16, **bf)
-        self.X = [self._x0_base[: self.P[0]]]
+        # two copies: batch i+1 is pre-processed into the other slot while step i trains (fl/trainer.py)
+        self._x0_bufs = [torch.zeros(self.P[0] + 8, 16, **bf) for _ in range(2)]
+        self.X0 = [b[: self.P[0]] for b in self._x0_bufs]
+        self._x0_base = self._x0_bufs[0]
+        self.X = [self.X0[0]]
         self.amax, self.dY, self.gX = [], [], [None]
         for l in range(self.n):
             hp = self.H[l + 1]
@@ -118,6 +121,7 @@ class MedCNNEngine:
         self.fused_step = False
         self.theta = torch.zeros(B, 2, 3, dtype=torch.float32, device=device)
         self.aug_seed = (cfg.seed * 2654435761 + 12345) & 0x7FFFFFFFFFFFFFFF or 1
+        self.prep_count = 0          # augmented batches pre-processed so far (keys the in-kernel Philox draw)
         # weight gradients run on a side stream, concurrently with the dgrad / un-pool chain
         self.side = torch.cuda.Stream(device)
         self.two_streams = True
@@ -157,15 +161,29 @@ class MedCNNEngine:
         th[:, 1, 1] = torch.cos(sh) * zy
         return th
 
-    def features(self, x_u8: torch.Tensor, train: bool, augment: bool) -> torch.Tensor:
-        # augmentation parameters are drawn inside the kernel (Philox keyed by seed and step)
-        seed = self.aug_seed if (train and augment) else 0
-        self.ops.preprocess_u8(x_u8, None, self.X[0], seed, self.step_ref)
+    def preprocess(self, x_u8: torch.Tensor, slot: int, train: bool, augment: bool) -> None:
+        """uint8 NHWC batch -> bf16 [P,16] layer-1 input of ``slot`` (1/255 rescale + Keras-style random
+        affine, FLPyfhelin.py:80-86). Augmentation parameters are drawn inside the kernel from Philox
+        keyed by (seed, number of augmented batches so far, sample): reproducible and independent of
+        which stream or slot the batch is staged on."""
+        seed = 0
+        if train and augment:
+            seed = (self.aug_seed + 0x9E3779B97F4A7C15 * (self.prep_count + 1)) & 0x7FFFFFFFFFFFFFFF or 1
+            self.prep_count += 1
+        self.ops.preprocess_u8(x_u8, None, self.X0[slot], seed, None)
+
+    def forward_convs(self, slot: int, train: bool) -> torch.Tensor:
+        x = self.X0[slot]
         for l in range(self.n):
             h = self.H[l]
-            self.ops.conv_fwd_pool(self.X[l], self._wf(l), self.bias[l], self.X[l + 1],
+            self.ops.conv_fwd_pool(x, self._wf(l), self.bias[l], self.X[l + 1],
                                    self.amax[l] if train else None, self.B, h, h, self.CK[l], self.Co[l])
+            x = self.X[l + 1]
         return self.X[self.n]
+
+    def features(self, x_u8: torch.Tensor, train: bool, augment: bool, slot: int = 0) -> torch.Tensor:
+        self.preprocess(x_u8, slot, train, augment)
+        return self.forward_convs(slot, train)
 
     def _head(self, feat: torch.Tensor) -> torch.Tensor:
         x = feat
@@ -176,7 +194,12 @@ class MedCNNEngine:
 
     # ------------------------------------------------------------------ steps
     def train_step(self, x_u8: torch.Tensor, y: torch.Tensor, out: torch.Tensor, augment: bool = True) -> None:
-        feat_bf = self.features(x_u8, True, augment)
+        self.preprocess(x_u8, 0, True, augment)
+        self.train_step_staged(0, y, out)
+
+    def train_step_staged(self, slot: int, y: torch.Tensor, out: torch.Tensor) -> None:
+        """Forward + backward on the already pre-processed batch in ``slot`` (CUDA-graph body)."""
+        feat_bf = self.forward_convs(slot, True)
         if self.fused_head:
             self.ops.head_forward_backward(feat_bf, self.pack.flat, self.pack.grad, self.head_offs, y, self.dfeat,
                                            self.h1_buf, self.dh1_buf, out, self.step_ref if self.fused_step else None,
@@ -195,8 +218,9 @@ class MedCNNEngine:
             h = self.H[l]
             if l == 0 and self.gather_wgrad0:
                 # 3-channel layer: weight gradient gathered straight from the pooled gradient
-                self.ops.wgrad0_gather(self._x0_base, g, self.amax[0], self._dw(0), self.B, h, h)
+                self.ops.wgrad0_gather(self._x0_bufs[slot], g, self.amax[0], self._dw(0), self.B, h, h)
                 break
+            xin = self.X0[slot] if l == 0 else self.X[l]
             if self.dY[l] is None:
                 self.dY[l] = torch.zeros(self.P[l], self.Co[l], dtype=torch.bfloat16, device=self.device)
             self.ops.unpool_relu(g, self.amax[l], self.X[l + 1], self.dY[l], self.B, h, h, self.Co[l])
@@ -204,9 +228,9 @@ class MedCNNEngine:
                 # wgrad(l) only needs X[l] and dY[l]; dgrad(l) -> unpool(l-1) -> ... proceeds meanwhile
                 self.side.wait_stream(main)
                 with torch.cuda.stream(self.side):
-                    self.ops.conv_wgrad(self.X[l], self.dY[l], self._dw(l), self.B, h, h, self.CK[l], self.Co[l])
+                    self.ops.conv_wgrad(xin, self.dY[l], self._dw(l), self.B, h, h, self.CK[l], self.Co[l])
             else:
-                self.ops.conv_wgrad(self.X[l], self.dY[l], self._dw(l), self.B, h, h, self.CK[l], self.Co[l])
+                self.ops.conv_wgrad(xin, self.dY[l], self._dw(l), self.B, h, h, self.CK[l], self.Co[l])
             if l > 0:
                 self.ops.conv_dgrad(self.dY[l], self._wd(l), self.gX[l], self.B, h, h, self.Co[l], self.Ci[l])
                 g = self.gX[l]
@@ -222,7 +246,11 @@ class MedCNNEngine:
                               self.pack.n_trainable)
 
     def eval_step(self, x_u8: torch.Tensor, y: torch.Tensor, out: torch.Tensor) -> None:
-        feat_bf = self.features(x_u8, False, False)
+        self.preprocess(x_u8, 0, False, False)
+        self.eval_step_staged(0, y, out)
+
+    def eval_step_staged(self, slot: int, y: torch.Tensor, out: torch.Tensor) -> None:
+        feat_bf = self.forward_convs(slot, False)
         if self.fused_head:
             self.ops.head_forward_backward(feat_bf, self.pack.flat, self.pack.grad, self.head_offs, y, self.dfeat,
                                            self.h1_buf, self.dh1_buf, out, None, self.B, self.F, self.H1, self.H2, self.C, False)

@@ -52,8 +52,9 @@ void preprocess_u8(const uint8_t* x, const float* theta, void* X, int B, int H, 
                    const int64_t* step, cudaStream_t st);
 void unpool_relu(const void* g, const uint8_t* amax, const void* ypool, void* dY, int B, int H, int W, int Hp,
                  int Wp, int Co, cudaStream_t st);
-void conv_weight_relayout(const void* shadow, const ConvLayerTable& t, void* Wf, void* Wd, cudaStream_t st);
-void conv_grad_finalize(float* dW32, const ConvLayerTable& t, float* grad, cudaStream_t st);
+void conv_weight_relayout(const void* shadow, const ConvLayerTable& t, void* Wf, void* Wd, int l0, int l1,
+                          cudaStream_t st);
+void conv_grad_finalize(float* dW32, const ConvLayerTable& t, float* grad, int l0, int l1, cudaStream_t st);
 void fused_update(float* dW32, const ConvLayerTable& t, float* flat, float* grad, float* m, float* v, void* shadow,
                   void* Wf, void* Wd, const int64_t* step, const float* lr_scale, float lr, float decay, float beta1,
                   float beta2, float eps, int64_t dense_off, int64_t n_trainable, cudaStream_t st);

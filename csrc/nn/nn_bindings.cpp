@@ -253,14 +253,22 @@ hefl::nn::ConvLayerTable table_from(const Tensor& t) {
   return T;
 }
 
-void conv_weight_relayout(const Tensor& shadow, const Tensor& table, Tensor Wf, Tensor Wd) {
+// l0/l1: layer range [l0, l1) (l1 = -1: all layers) so the update of the layers whose gradients are final can
+// run on a side stream under the last weight-gradient kernel.
+void conv_weight_relayout(const Tensor& shadow, const Tensor& table, Tensor Wf, Tensor Wd, int64_t l0, int64_t l1) {
   chk_bf16(shadow, "shadow"); chk_bf16(Wf, "Wf"); chk_bf16(Wd, "Wd");
-  hefl::nn::conv_weight_relayout(shadow.data_ptr(), table_from(table), Wf.data_ptr(), Wd.data_ptr(), cur());
+  const auto t = table_from(table);
+  if (l1 < 0) l1 = t.n;
+  TORCH_CHECK(0 <= l0 && l1 <= t.n, "layer range");
+  hefl::nn::conv_weight_relayout(shadow.data_ptr(), t, Wf.data_ptr(), Wd.data_ptr(), (int)l0, (int)l1, cur());
 }
 
-void conv_grad_finalize(Tensor dW32, const Tensor& table, Tensor grad) {
+void conv_grad_finalize(Tensor dW32, const Tensor& table, Tensor grad, int64_t l0, int64_t l1) {
   TORCH_CHECK(dW32.is_cuda() && dW32.scalar_type() == at::kFloat && grad.is_cuda() && grad.scalar_type() == at::kFloat, "float32 CUDA tensors required");
-  hefl::nn::conv_grad_finalize(dW32.data_ptr<float>(), table_from(table), grad.data_ptr<float>(), cur());
+  const auto t = table_from(table);
+  if (l1 < 0) l1 = t.n;
+  TORCH_CHECK(0 <= l0 && l1 <= t.n, "layer range");
+  hefl::nn::conv_grad_finalize(dW32.data_ptr<float>(), t, grad.data_ptr<float>(), (int)l0, (int)l1, cur());
 }
 
 }  // namespace
@@ -283,6 +291,6 @@ TORCH_LIBRARY_FRAGMENT(hefl, m) {
   m.def("avgpool_forward(Tensor x, Tensor(a!) out, int B, int HW, int C) -> ()", &avgpool_forward);
   m.def("avgpool_backward(Tensor dout, Tensor(a!) dx, int B, int HW, int C) -> ()", &avgpool_backward);
   m.def("umma_shift_probe(Tensor A, Tensor Bm, int CK, int shift_rows, int mode) -> Tensor", &umma_shift_probe);
-  m.def("conv_weight_relayout(Tensor shadow, Tensor table, Tensor(a!) Wf, Tensor(b!) Wd) -> ()", &conv_weight_relayout);
-  m.def("conv_grad_finalize(Tensor(a!) dW32, Tensor table, Tensor(b!) grad) -> ()", &conv_grad_finalize);
+  m.def("conv_weight_relayout(Tensor shadow, Tensor table, Tensor(a!) Wf, Tensor(b!) Wd, int l0=0, int l1=-1) -> ()", &conv_weight_relayout);
+  m.def("conv_grad_finalize(Tensor(a!) dW32, Tensor table, Tensor(b!) grad, int l0=0, int l1=-1) -> ()", &conv_grad_finalize);
 }

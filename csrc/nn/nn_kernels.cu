@@ -197,9 +197,9 @@ void unpool_relu(const void* g, const uint8_t* amax, const void* ypool, void* dY
 // bf16 shadow of the flat parameters ([Co][Ci][3][3] per conv) -> Wf [tap][Co][CK] (forward B
 // operand, channel-padded) and Wd [tap][Ci][Co] (dgrad B operand).
 __global__ void conv_weight_relayout_kernel(const __nv_bfloat16* __restrict__ shadow, const ConvLayerTable t,
-                                            __nv_bfloat16* __restrict__ Wf, __nv_bfloat16* __restrict__ Wd) {
+                                            __nv_bfloat16* __restrict__ Wf, __nv_bfloat16* __restrict__ Wd, int l0) {
   pdl_wait();   // parameter writer: no early trigger (see launch.cuh)
-  const int l = blockIdx.y;
+  const int l = blockIdx.y + l0;
   const int Ci = t.Ci[l], CK = t.CK[l], Co = t.Co[l];
   const __nv_bfloat16* w = shadow + t.w_off[l];
   const int nf = 9 * Co * CK;
@@ -216,20 +216,22 @@ __global__ void conv_weight_relayout_kernel(const __nv_bfloat16* __restrict__ sh
   }
 }
 
-void conv_weight_relayout(const void* shadow, const ConvLayerTable& t, void* Wf, void* Wd, cudaStream_t st) {
-  dim3 grid(32, t.n);
+void conv_weight_relayout(const void* shadow, const ConvLayerTable& t, void* Wf, void* Wd, int l0, int l1,
+                          cudaStream_t st) {
+  if (l1 <= l0) return;
+  dim3 grid(32, l1 - l0);
   launch_pdl(conv_weight_relayout_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(shadow), t,
                                                     reinterpret_cast<__nv_bfloat16*>(Wf),
-                                                    reinterpret_cast<__nv_bfloat16*>(Wd));
+                                                    reinterpret_cast<__nv_bfloat16*>(Wd), l0);
   hefl::cuda::note_launch();
 }
 
 // dW32 [9*CK+1][Co] (wgrad output, row 9*CK = bias gradient) -> flat fp32 gradient in the
 // parameter layout ([Co][Ci][3][3], then bias); clears dW32 for the next step.
 __global__ void conv_grad_finalize_kernel(float* __restrict__ dW32, const ConvLayerTable t,
-                                          float* __restrict__ grad) {
+                                          float* __restrict__ grad, int l0) {
   pdl_prologue();
-  const int l = blockIdx.y;
+  const int l = blockIdx.y + l0;
   const int Ci = t.Ci[l], CK = t.CK[l], Co = t.Co[l];
   float* src = dW32 + t.dw_off[l];
   const int nw = Co * Ci * 9;
@@ -245,12 +247,14 @@ __global__ void zero_f32_kernel(float* __restrict__ p, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0.f;
 }
 
-void conv_grad_finalize(float* dW32, const ConvLayerTable& t, float* grad, cudaStream_t st) {
-  dim3 grid(32, t.n);
-  launch_pdl(conv_grad_finalize_kernel, dim3(grid), dim3(256), 0, st, dW32, t, grad);
-  const int l = t.n - 1;
-  const int64_t total = t.dw_off[l] + (int64_t)(9 * t.CK[l] + 1) * t.Co[l];
-  launch_pdl(zero_f32_kernel, dim3(64), dim3(256), 0, st, dW32, total);
+void conv_grad_finalize(float* dW32, const ConvLayerTable& t, float* grad, int l0, int l1, cudaStream_t st) {
+  if (l1 <= l0) return;
+  dim3 grid(32, l1 - l0);
+  launch_pdl(conv_grad_finalize_kernel, dim3(grid), dim3(256), 0, st, dW32, t, grad, l0);
+  const int l = l1 - 1;
+  const int64_t begin = t.dw_off[l0];
+  const int64_t total = t.dw_off[l] + (int64_t)(9 * t.CK[l] + 1) * t.Co[l] - begin;
+  launch_pdl(zero_f32_kernel, dim3(64), dim3(256), 0, st, dW32 + begin, total);
   hefl::cuda::note_launch(2);
 }
 

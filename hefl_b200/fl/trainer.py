@@ -74,6 +74,11 @@ class LocalTrainer:
             # staged input pipeline: batch i+1 is pre-processed into the other X0 slot on `prep_stream`
             # while the graph of step i runs; one captured graph per (train/eval, slot)
             self.static_y2 = [torch.zeros(B, dtype=torch.int64, device=device) for _ in range(2)]
+            # per-slot result buffers: the D2H read of step i runs on `stats_stream` under step i+1
+            self.out_train2 = [self.out_train, torch.zeros(2, dtype=torch.float32, device=device)]
+            self.out_eval2 = [self.out_eval, torch.zeros(2, dtype=torch.float32, device=device)]
+            self.stats_stream = torch.cuda.Stream(device)
+            self._stats_done = [torch.cuda.Event() for _ in range(2)]
             self._graphs: Dict[Tuple[bool, int], torch.cuda.CUDAGraph] = {}
             self.prep_stream = torch.cuda.Stream(device)
             self._slot_ready = [torch.cuda.Event() for _ in range(2)]
@@ -94,6 +99,9 @@ class LocalTrainer:
         return self.model(x)
 
     def _train_eager(self, x_u8: torch.Tensor, y: torch.Tensor) -> None:
+        if self.engine is not None and not self.engine.fused_step:
+            self.engine.train_step(x_u8, y, self.out_train, augment=self.augment, opt=self)
+            return
         if self.engine is not None:
             self.engine.train_step(x_u8, y, self.out_train, augment=self.augment)
         else:
@@ -106,8 +114,22 @@ class LocalTrainer:
 
     def _train_staged(self, slot: int) -> None:
         """Graph body of the tcgen05 engine: forward/backward on the pre-processed batch of ``slot`` + update."""
-        self.engine.train_step_staged(slot, self.static_y2[slot], self.out_train)
-        self._optimizer_step()
+        if self.engine.fused_step:
+            self.engine.train_step_staged(slot, self.static_y2[slot], self.out_train2[slot])
+            self._optimizer_step()
+        else:
+            self.engine.train_step_staged(slot, self.static_y2[slot], self.out_train2[slot], opt=self)
+
+    # update hooks driven by the engine (it knows when each layer's gradient is final)
+    def bump(self) -> None:
+        self.step_t += 1
+
+    def apply(self, lo: int, hi: int) -> None:
+        c = self.cfg
+        if hi <= lo:
+            return
+        self.ops.adam_step_(self.pack.trainable()[lo:hi], self.pack.grad[lo:hi], self.m[lo:hi], self.v[lo:hi],
+                            self.engine.shadow[lo:hi], self.step_t, self.lr_scale, c.lr, c.lr_decay, 0.9, 0.999, 1e-7)
 
     def _optimizer_step(self) -> None:
         c = self.cfg
@@ -145,7 +167,7 @@ class LocalTrainer:
                 if eng is not None:
                     for slot in range(2):
                         self._train_staged(slot)
-                        eng.eval_step_staged(slot, self.static_y2[slot], self.out_eval)
+                        eng.eval_step_staged(slot, self.static_y2[slot], self.out_eval2[slot])
                 else:
                     self._train_eager(self.static_x, self.static_y)
                     self._eval_eager(self.static_x, self.static_y)
@@ -163,7 +185,7 @@ class LocalTrainer:
                             self._train_staged(slot)
                         else:
                             with torch.no_grad():
-                                eng.eval_step_staged(slot, self.static_y2[slot], self.out_eval)
+                                eng.eval_step_staged(slot, self.static_y2[slot], self.out_eval2[slot])
                     self._graphs[(train, slot)] = g
                     counts[(train, slot)] = int(self.ops.launch_count()) - a
             self._graph_train, self._graph_eval = self._graphs[(True, 0)], self._graphs[(False, 0)]
@@ -231,13 +253,15 @@ class LocalTrainer:
             return
         if not self._graphs:
             self._capture()
-        main, prep = torch.cuda.current_stream(self.device), self.prep_stream
+        main, prep, sst = torch.cuda.current_stream(self.device), self.prep_stream, self.stats_stream
         prep.wait_stream(main)
         for ev in self._slot_free:
             ev.record(main)
+        for ev in self._stats_done:
+            ev.record(main)
         it = iter(feeder.epoch())
         n = feeder.steps
-        out = self.out_train if train else self.out_eval
+        outs = self.out_train2 if train else self.out_eval2
 
         def stage(slot: int) -> None:
             with torch.cuda.stream(prep):
@@ -253,14 +277,19 @@ class LocalTrainer:
             if i + 1 < n:
                 stage(slot ^ 1)
             main.wait_event(self._slot_ready[slot])
+            main.wait_event(self._stats_done[slot])           # result buffer of this slot has been read back
             self._graphs[(train, slot)].replay()
             self._slot_free[slot].record(main)
-            stats[i].copy_(out, non_blocking=True)
+            with torch.cuda.stream(sst):                      # D2H of the step's loss/accuracy, off the main stream
+                sst.wait_event(self._slot_free[slot])
+                stats[i].copy_(outs[slot], non_blocking=True)
+                self._stats_done[slot].record(sst)
         self.replayed_launches += n * self.graph_launches[0 if train else 1]
         with torch.cuda.stream(prep):
             for _ in it:                                      # let the feeder finish its bookkeeping
                 pass
         main.wait_stream(prep)
+        main.wait_stream(sst)
 
     def fit(self, train: BatchFeeder, val: Optional[BatchFeeder], epochs: int,
             early_stopping: Optional[int] = 5, restore_best: bool = True,

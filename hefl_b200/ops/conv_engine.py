@@ -102,6 +102,10 @@ class MedCNNEngine:
             self.b_off.append(offs[kb])
         self.table = torch.tensor(rows, dtype=torch.int64)
         self.bias = [pack.flat[self.b_off[l]: self.b_off[l] + self.Co[l]] for l in range(self.n)]
+        # flat parameters [0, p0) belong to layer 1 (weights then bias come first in the pack)
+        self.p0 = max(offs[conv_keys[0][0]] + 9 * self.Ci[0] * self.Co[0], self.b_off[0] + self.Co[0])
+        if self.n > 1 and not (self.p0 <= offs[conv_keys[1][0]] and self.p0 <= self.b_off[1]):
+            self.p0 = 0          # unexpected parameter order: never split the update
         # dense head: fused kernels when it is the reference's 3-layer shape, else PyTorch autograd
         fcs = list(model.fcs)
         self.fused_head = len(fcs) == 3 and B <= 32 and B % 2 == 0
@@ -118,7 +122,7 @@ class MedCNNEngine:
         # parameters as one contiguous tail of the flat buffer
         self.dense_off = min(self.head_offs) if self.fused_head else 0
         # measured: 43 us fused (scattered m/v/flat accesses) vs 24 us for finalize+Adam+relayout -> off by default
-        self.fused_step = False
+        self.fused_step = os.environ.get("HEFL_FUSED_STEP", "0") == "1" and self.fused_head
         self.theta = torch.zeros(B, 2, 3, dtype=torch.float32, device=device)
         self.aug_seed = (cfg.seed * 2654435761 + 12345) & 0x7FFFFFFFFFFFFFFF or 1
         self.prep_count = 0          # augmented batches pre-processed so far (keys the in-kernel Philox draw)
@@ -193,12 +197,17 @@ class MedCNNEngine:
         return fcs[-1](x)
 
     # ------------------------------------------------------------------ steps
-    def train_step(self, x_u8: torch.Tensor, y: torch.Tensor, out: torch.Tensor, augment: bool = True) -> None:
+    def train_step(self, x_u8: torch.Tensor, y: torch.Tensor, out: torch.Tensor, augment: bool = True, opt=None) -> None:
         self.preprocess(x_u8, 0, True, augment)
-        self.train_step_staged(0, y, out)
+        self.train_step_staged(0, y, out, opt)
 
-    def train_step_staged(self, slot: int, y: torch.Tensor, out: torch.Tensor) -> None:
-        """Forward + backward on the already pre-processed batch in ``slot`` (CUDA-graph body)."""
+    def train_step_staged(self, slot: int, y: torch.Tensor, out: torch.Tensor, opt=None) -> None:
+        """Forward + backward on the already pre-processed batch in ``slot`` (CUDA-graph body).
+
+        ``opt`` (optional) applies the parameter update: ``opt.bump()`` advances the step counter and
+        ``opt.apply(lo, hi)`` runs Adam on flat parameters [lo, hi). With two streams, everything but
+        layer 1 is updated on the side stream while layer 1's weight-gradient kernel still runs; only
+        the 896 layer-1 parameters are left for the tail of the step."""
         feat_bf = self.forward_convs(slot, True)
         if self.fused_head:
             self.ops.head_forward_backward(feat_bf, self.pack.flat, self.pack.grad, self.head_offs, y, self.dfeat,
@@ -214,9 +223,20 @@ class MedCNNEngine:
             out[1] = (logits.argmax(1) == y).sum()
             g = feat.grad.to(torch.bfloat16).view_as(feat_bf).contiguous()
         main = torch.cuda.current_stream(self.device)
+        split = False
         for l in range(self.n - 1, -1, -1):
             h = self.H[l]
             if l == 0 and self.gather_wgrad0:
+                if opt is not None and self.two_streams and not self.fused_step and self.n > 1 and self.p0 > 0:
+                    split = True
+                    ev = torch.cuda.Event()
+                    ev.record(main)                     # dgrad of layer 2 (last reader of Wd) is enqueued
+                    with torch.cuda.stream(self.side):
+                        self.side.wait_event(ev)
+                        opt.bump()
+                        self.ops.conv_grad_finalize(self.dW32, self.table, self.pack.grad, 1, self.n)
+                        opt.apply(self.p0, self.pack.n_trainable)
+                        self.ops.conv_weight_relayout(self.shadow, self.table, self.Wf, self.Wd, 1, self.n)
                 # 3-channel layer: weight gradient gathered straight from the pooled gradient
                 self.ops.wgrad0_gather(self._x0_bufs[slot], g, self.amax[0], self._dw(0), self.B, h, h)
                 break
@@ -236,8 +256,19 @@ class MedCNNEngine:
                 g = self.gX[l]
         if self.two_streams:
             main.wait_stream(self.side)
-        if not self.fused_step:
+        if self.fused_step:
+            return
+        if opt is None:
             self.ops.conv_grad_finalize(self.dW32, self.table, self.pack.grad)
+        elif split:
+            self.ops.conv_grad_finalize(self.dW32, self.table, self.pack.grad, 0, 1)
+            opt.apply(0, self.p0)
+            self.ops.conv_weight_relayout(self.shadow, self.table, self.Wf, self.Wd, 0, 1)
+        else:
+            opt.bump()
+            self.ops.conv_grad_finalize(self.dW32, self.table, self.pack.grad)
+            opt.apply(0, self.pack.n_trainable)
+            self.after_update()
 
     def fused_update(self, m: torch.Tensor, v: torch.Tensor, step: torch.Tensor, lr_scale: torch.Tensor, cfg) -> None:
         """finalize + Adam + bf16 shadow + tensor-core weight layouts + dW32 clear, one launch."""

@@ -26,6 +26,11 @@ void head_forward_backward(const void* feat, const float* W1, const float* b1, c
                            float* gb2, float* gW3, float* gb3, void* dfeat, float* h1_buf, float* dh1_buf,
                            float* out, int64_t* step, int B, int F, int H1, int H2, int C, int train, cudaStream_t st);
 void set_pdl(int on);
+bool head_cluster_supported(int B, int F, int H1, int H2, int C);
+void head_cluster(const void* feat, const float* W1, const float* b1, const float* W2, const float* b2,
+                  const float* W3, const float* b3, const int64_t* y, float* gW1, float* gb1, float* gW2, float* gb2,
+                  float* gW3, float* gb3, void* dfeat, float* out, int64_t* step, int B, int C, int train,
+                  cudaStream_t st);
 bool wgrad0_gather_supported(int W, int Wp, int CK, int Ci, int Co);
 void wgrad0_gather(const void* X, const void* g, const uint8_t* amax, float* dW, int B, int H, int W, int Hp, int Wp,
                    cudaStream_t st);

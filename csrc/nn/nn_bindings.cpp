@@ -139,6 +139,8 @@ void unpool_relu(const Tensor& g, const Tensor& amax, const Tensor& ypool, Tenso
                         (int)W, (int)Hp, (int)Wp, (int)Co, cur());
 }
 
+static int g_head_cluster = 1;
+
 // flat / grad are the ParamPack buffers; offs = [W1, b1, W2, b2, W3, b3] element offsets.
 void head_forward_backward(const Tensor& feat, const Tensor& flat, Tensor grad, at::IntArrayRef offs, const Tensor& y,
                            Tensor dfeat, Tensor h1_buf, Tensor dh1_buf, Tensor out, const c10::optional<Tensor>& step,
@@ -150,9 +152,17 @@ void head_forward_backward(const Tensor& feat, const Tensor& flat, Tensor grad, 
   TORCH_CHECK(flat.is_cuda() && flat.scalar_type() == at::kFloat && grad.scalar_type() == at::kFloat, "float32 parameter buffers required");
   TORCH_CHECK(y.is_cuda() && y.scalar_type() == at::kLong && y.numel() == B, "labels must be int64 [B]");
   TORCH_CHECK(h1_buf.numel() >= B * H1 && dh1_buf.numel() >= B * (H1 + H2) && out.numel() >= 2, "scratch too small");
-  TORCH_CHECK(B % 2 == 0 && H2 % 4 == 0 && H1 % 4 == 0 && F % 8 == 0, "head dims must be even / multiples of 4 / 8");
   const float* p = flat.data_ptr<float>();
   float* g = grad.data_ptr<float>();
+  if (g_head_cluster && hefl::nn::head_cluster_supported((int)B, (int)F, (int)H1, (int)H2, (int)C)) {
+    // one launch on a cluster of 8 CTAs (csrc/nn/head_cluster.cu)
+    hefl::nn::head_cluster(feat.data_ptr(), p + offs[0], p + offs[1], p + offs[2], p + offs[3], p + offs[4], p + offs[5],
+                           y.data_ptr<int64_t>(), g + offs[0], g + offs[1], g + offs[2], g + offs[3], g + offs[4],
+                           g + offs[5], dfeat.data_ptr(), out.data_ptr<float>(),
+                           step.has_value() ? step->data_ptr<int64_t>() : nullptr, (int)B, (int)C, train ? 1 : 0, cur());
+    return;
+  }
+  TORCH_CHECK(B % 2 == 0 && H2 % 4 == 0 && H1 % 4 == 0 && F % 8 == 0, "head dims must be even / multiples of 4 / 8");
   hefl::nn::head_forward_backward(feat.data_ptr(), p + offs[0], p + offs[1], p + offs[2], p + offs[3], p + offs[4],
                                   p + offs[5], y.data_ptr<int64_t>(), g + offs[0], g + offs[1], g + offs[2],
                                   g + offs[3], g + offs[4], g + offs[5], dfeat.data_ptr(), h1_buf.data_ptr<float>(),
@@ -284,6 +294,7 @@ TORCH_LIBRARY_FRAGMENT(hefl, m) {
   m.def("head_forward_backward(Tensor feat, Tensor flat, Tensor(a!) grad, int[] offs, Tensor y, Tensor(b!) dfeat, Tensor(c!) h1_buf, Tensor(d!) dh1_buf, Tensor(e!) out, Tensor(f!)? step, int B, int F, int H1, int H2, int C, bool train) -> ()", &head_forward_backward);
   m.def("fused_update(Tensor(a!) dW32, Tensor table, Tensor(b!) flat, Tensor(c!) grad, Tensor(d!) m, Tensor(e!) v, Tensor(f!) shadow, Tensor(g!) Wf, Tensor(h!) Wd, Tensor step, Tensor? lr_scale, float lr, float decay, float beta1, float beta2, float eps, int dense_off, int n_trainable) -> ()", &fused_update);
   m.def("conv_set_debug(int mask) -> ()", &conv_set_debug);
+  m.def("set_head_cluster(int on) -> ()", [](int64_t on) { g_head_cluster = (int)on; });
   m.def("set_pdl(int on) -> ()", [](int64_t on) { hefl::nn::set_pdl((int)on); });
   m.def("wgrad0_gather(Tensor X, Tensor g, Tensor amax, Tensor(a!) dW32, int B, int H, int W) -> ()", &wgrad0_gather);
   m.def("bn_forward(Tensor x, Tensor? res, Tensor gamma, Tensor beta, Tensor(a!)? run_mean, Tensor(b!)? run_var, Tensor(c!) mean, Tensor(d!) invstd, Tensor(e!) sums, Tensor(f!) y, float momentum, float eps, bool relu) -> ()", &bn_forward);

@@ -43,6 +43,7 @@ CUDA_SOURCES = [
     "nn/nn_kernels.cu",
     "nn/resnet_kernels.cu",
     "nn/wgrad_gather.cu",
+    "nn/head_cluster.cu",
 ]
 HOST_SOURCES = [
     "he/host_math.cpp",

@@ -37,6 +37,7 @@ class MedCNNEngine:
         if device.type != "cuda":
             raise RuntimeError("the tcgen05 engine needs a CUDA device (sm_100a)")
         self.ops = _ext.ops()
+        self.ops.set_head_cluster(0 if os.environ.get("HEFL_HEAD_CLUSTER", "1") == "0" else 1)
         self.ops.set_pdl(0 if os.environ.get("HEFL_PDL", "1") == "0" else 1)   # programmatic dependent launch
         self.model, self.pack, self.cfg, self.device = model, pack, cfg, device
         B, S = cfg.batch_size, cfg.image_size

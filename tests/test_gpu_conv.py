@@ -135,6 +135,50 @@ def test_preprocess_matches_grid_sample():
     assert (X.view(B, H, H, 16)[..., :3].float() - ref).abs().max() < 1e-2
 
 
+@pytest.mark.parametrize("cluster", [1, 0])
+@pytest.mark.parametrize("B,C,train", [(32, 2, True), (8, 2, True), (32, 3, True), (16, 2, False)])
+def test_head_matches_autograd(cluster, B, C, train):
+    """Dense head fwd+bwd (cluster kernel and the 4-kernel fallback) vs PyTorch fp32 autograd."""
+    Fdim, H1, H2 = 512, 128, 64
+    g = torch.Generator(device="cuda").manual_seed(21)
+    sizes = [H1 * Fdim, H1, H2 * H1, H2, C * H2, C]
+    offs = [0]
+    for n in sizes[:-1]:
+        offs.append(offs[-1] + n)
+    flat = torch.randn(sum(sizes), device="cuda", generator=g) * 0.05
+    grad = torch.zeros_like(flat)
+    feat = _bf(torch.rand(B, Fdim, device="cuda", generator=g))
+    y = torch.randint(0, C, (B,), device="cuda", generator=g)
+    dfeat = torch.zeros(B, Fdim, dtype=torch.bfloat16, device="cuda")
+    h1_buf = torch.zeros(B * H1, device="cuda")
+    dh1_buf = torch.zeros(B * (H1 + H2), device="cuda")
+    out = torch.zeros(2, device="cuda")
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ops.set_head_cluster(cluster)
+    try:
+        ops.head_forward_backward(feat, flat, grad, offs, y, dfeat, h1_buf, dh1_buf, out, step, B, Fdim, H1, H2, C, train)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_head_cluster(1)
+    ps = [flat[o:o + n].clone().requires_grad_(True) for o, n in zip(offs, sizes)]
+    x = feat.float().requires_grad_(True)
+    h = F.relu(F.linear(x, ps[0].view(H1, Fdim), ps[1]))
+    h = F.relu(F.linear(h, ps[2].view(H2, H1), ps[3]))
+    logits = F.linear(h, ps[4].view(C, H2), ps[5])
+    loss = F.cross_entropy(logits, y)
+    assert abs(float(out[0]) - float(loss.detach())) < 1e-4
+    assert int(out[1]) == int((logits.argmax(1) == y).sum())
+    if not train:
+        assert int(step) == 0 and float(grad.abs().max()) == 0.0
+        return
+    assert int(step) == 1
+    loss.backward()
+    for o, n, p_ in zip(offs, sizes, ps):
+        ref = p_.grad
+        assert (grad[o:o + n] - ref).abs().max() <= 1e-4 * ref.abs().max() + 1e-7
+    assert (dfeat.float() - x.grad).abs().max() <= 1e-2 * x.grad.abs().max() + 1e-7
+
+
 @pytest.mark.parametrize("H", [256, 66])
 def test_wgrad0_gather_matches_autograd(H):
     """Layer-1 weight/bias gradient gathered from the pooled gradient == autograd through

@@ -119,8 +119,12 @@ struct TapGemmArgs {
   uint8_t* argmax;      // POOL, may be null
 };
 
-template <int CK, int CO, bool POOL>
+// TS = filter taps along the image row that are separate GEMMs: 3 normally; 1 when the three horizontal taps
+// are packed into the channel dimension by the producer of the input (layer 1: 3 channels x 3 taps = 9 of the
+// 16 padded channels, written by preprocess_u8) — a third of the MMAs for the same bytes.
+template <int CK, int CO, bool POOL, int TS = 3>
 struct TapGemmCfg {
+  static constexpr int NTAP = 3 * TS;
   static constexpr int KB = CK < 64 ? CK : 64;            // channels per k-block (one swizzle atom)
   static constexpr int NKB = CK / KB;
   static constexpr int ROW_BYTES = KB * 2;
@@ -131,7 +135,7 @@ struct TapGemmCfg {
   static constexpr int HALO = NKB * NSEG * SEG_BYTES;     // one tile's input
   static constexpr int W_SUB = CO * ROW_BYTES;
   static constexpr int W_TAP = W_SUB * NKB;
-  static constexpr int W_BYTES = 9 * W_TAP;
+  static constexpr int W_BYTES = NTAP * W_TAP;
   static constexpr int BAR_BYTES = 384;
   static constexpr int BUDGET = 225 * 1024;
   static constexpr int NBUF_RAW = (BUDGET - W_BYTES - BAR_BYTES - 1024) / HALO;
@@ -156,11 +160,11 @@ struct TapGemmCfg {
   static_assert(CO % 32 == 0 && CO <= 128, "CO must be 32, 64, 96 or 128");
 };
 
-template <int CK, int CO, bool POOL>
-__global__ void __launch_bounds__(352, TapGemmCfg<CK, CO, POOL>::OCC)
+template <int CK, int CO, bool POOL, int TS>
+__global__ void __launch_bounds__(352, TapGemmCfg<CK, CO, POOL, TS>::OCC)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                 const TapGemmArgs a) {
-  using Cfg = TapGemmCfg<CK, CO, POOL>;
+  using Cfg = TapGemmCfg<CK, CO, POOL, TS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;
@@ -195,7 +199,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   pdl_trigger();
   if (warp == 8 && elect_one()) {
     mbar_expect_tx(wfull, Cfg::W_BYTES);
-    for (int tap = 0; tap < 9; ++tap)
+    for (int tap = 0; tap < Cfg::NTAP; ++tap)
       for (int kb = 0; kb < Cfg::NKB; ++kb)
         tma_load_2d(sW + tap * Cfg::W_TAP + kb * Cfg::W_SUB, &tmW, kb * Cfg::KB,
                     tap * a.co_total + blockIdx.y * CO, wfull);
@@ -261,8 +265,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (j != jme || (a.dbg & 2)) continue;
           const uint32_t d_tmem = tmem_base + (tb * Cfg::NACC + j) * CO;
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const int r = tap / 3, s = tap % 3;
+          for (int tap = 0; tap < Cfg::NTAP; ++tap) {
+            const int r = tap / TS, s = tap % TS;
             const int seg = POOL ? (j + r) : r;
             const int shift = POOL ? s : (2 - s);
 #pragma unroll
@@ -374,12 +378,12 @@ done_roles:
   }
 }
 
-template <int CK, int CO, bool POOL>
+template <int CK, int CO, bool POOL, int TS = 3>
 static void launch_tap_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Wt, TapGemmArgs a, cudaStream_t st) {
-  using Cfg = TapGemmCfg<CK, CO, POOL>;
+  using Cfg = TapGemmCfg<CK, CO, POOL, TS>;
   const CUtensorMap tmA = make_map(A, CK, (uint64_t)a.P, (uint64_t)CK * 2, Cfg::KB, Cfg::SEG_ROWS);
-  const CUtensorMap tmW = make_map(Wt, CK, (uint64_t)9 * a.co_total, (uint64_t)CK * 2, Cfg::KB, CO);
-  auto kern = tap_gemm_kernel<CK, CO, POOL>;
+  const CUtensorMap tmW = make_map(Wt, CK, (uint64_t)Cfg::NTAP * a.co_total, (uint64_t)CK * 2, Cfg::KB, CO);
+  auto kern = tap_gemm_kernel<CK, CO, POOL, TS>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   const int ny = a.co_total / CO;
   const int slots = num_sms() * Cfg::OCC / ny;
@@ -394,7 +398,7 @@ static int g_dbg = 0;
 void conv_set_debug(int mask) { g_dbg = mask; }
 
 void conv_fwd_pool(const void* X, const void* Wf, const float* bias, void* out, uint8_t* argmax, int B, int H,
-                   int W, int CK, int CO, cudaStream_t st) {
+                   int W, int CK, int CO, int spack, cudaStream_t st) {
   TapGemmArgs a{};
   a.dbg = g_dbg;
   a.B = B; a.H = H; a.W = W;
@@ -408,7 +412,8 @@ void conv_fwd_pool(const void* X, const void* Wf, const float* bias, void* out, 
   a.argmax = argmax;
   const auto* x = reinterpret_cast<const __nv_bfloat16*>(X);
   const auto* w = reinterpret_cast<const __nv_bfloat16*>(Wf);
-  if (CK == 16 && CO == 32) launch_tap_gemm<16, 32, true>(x, w, a, st);
+  if (CK == 16 && CO == 32 && spack) launch_tap_gemm<16, 32, true, 1>(x, w, a, st);
+  else if (CK == 16 && CO == 32) launch_tap_gemm<16, 32, true>(x, w, a, st);
   else if (CK == 32 && CO == 32) launch_tap_gemm<32, 32, true>(x, w, a, st);
   else if (CK == 32 && CO == 64) launch_tap_gemm<32, 64, true>(x, w, a, st);
   else if (CK == 64 && CO == 64) launch_tap_gemm<64, 64, true>(x, w, a, st);

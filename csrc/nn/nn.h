@@ -15,7 +15,7 @@ void adam_step(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_
 
 // ---- tcgen05 implicit-GEMM convolution (conv_tcgen05.cu) ----
 void conv_fwd_pool(const void* X, const void* Wf, const float* bias, void* out, uint8_t* argmax, int B, int H,
-                   int W, int CK, int CO, cudaStream_t st);
+                   int W, int CK, int CO, int spack, cudaStream_t st);
 void conv_set_debug(int mask);
 void conv_dgrad(const void* dY, const void* Wd, void* dX, int B, int H, int W, int CK, int CO, cudaStream_t st);
 void conv_wgrad(const void* X, const void* DY, float* dW32, int B, int H, int W, int CK, int Co, cudaStream_t st);
@@ -54,11 +54,11 @@ struct ConvLayerTable {
   int64_t dw_off[kMaxConvLayers];                             // offsets (elements) into the fp32 dW32 buffer
 };
 void preprocess_u8(const uint8_t* x, const float* theta, void* X, int B, int H, int W, uint64_t aug_seed,
-                   const int64_t* step, cudaStream_t st);
+                   const int64_t* step, int spack, cudaStream_t st);
 void unpool_relu(const void* g, const uint8_t* amax, const void* ypool, void* dY, int B, int H, int W, int Hp,
                  int Wp, int Co, cudaStream_t st);
 void conv_weight_relayout(const void* shadow, const ConvLayerTable& t, void* Wf, void* Wd, int l0, int l1,
-                          cudaStream_t st);
+                          int spack0, cudaStream_t st);
 void conv_grad_finalize(float* dW32, const ConvLayerTable& t, float* grad, int l0, int l1, cudaStream_t st);
 void fused_update(float* dW32, const ConvLayerTable& t, float* flat, float* grad, float* m, float* v, void* shadow,
                   void* Wf, void* Wd, const int64_t* step, const float* lr_scale, float lr, float decay, float beta1,

@@ -77,10 +77,12 @@ inline void chk_bf16(const Tensor& t, const char* n) {
 }
 
 void conv_fwd_pool(const Tensor& X, const Tensor& Wf, const Tensor& bias, Tensor out,
-                   const c10::optional<Tensor>& argmax, int64_t B, int64_t H, int64_t W, int64_t CK, int64_t CO) {
+                   const c10::optional<Tensor>& argmax, int64_t B, int64_t H, int64_t W, int64_t CK, int64_t CO,
+                   bool spack) {
   chk_bf16(X, "X"); chk_bf16(Wf, "Wf"); chk_bf16(out, "out");
   TORCH_CHECK(X.numel() == B * H * W * CK, "X must be [B*H*W, CK]");
-  TORCH_CHECK(Wf.numel() == 9 * CO * CK, "Wf must be [9, CO, CK]");
+  TORCH_CHECK(Wf.numel() >= (spack ? 3 : 9) * CO * CK, "Wf must be [9, CO, CK] ([3, CO, CK] s-packed)");
+  TORCH_CHECK(!spack || (CK == 16 && CO == 32), "s-packed input is the 3-channel first layer only");
   TORCH_CHECK(bias.is_cuda() && bias.scalar_type() == at::kFloat && bias.numel() == CO, "bias must be float32 [CO]");
   const int64_t Hp = (H - 2) / 2, Wp = (W - 2) / 2;
   TORCH_CHECK(out.numel() == B * Hp * Wp * CO, "out must be [B,Hp,Wp,CO]");
@@ -90,7 +92,7 @@ void conv_fwd_pool(const Tensor& X, const Tensor& Wf, const Tensor& bias, Tensor
     am = argmax->data_ptr<uint8_t>();
   }
   hefl::nn::conv_fwd_pool(X.data_ptr(), Wf.data_ptr(), bias.data_ptr<float>(), out.data_ptr(), am, (int)B, (int)H,
-                          (int)W, (int)CK, (int)CO, cur());
+                          (int)W, (int)CK, (int)CO, spack ? 1 : 0, cur());
 }
 
 void conv_dgrad(const Tensor& dY, const Tensor& Wd, Tensor dX, int64_t B, int64_t H, int64_t W, int64_t CK,
@@ -109,7 +111,7 @@ void conv_wgrad(const Tensor& X, const Tensor& DY, Tensor dW32, int64_t B, int64
 }
 
 void preprocess_u8(const Tensor& x, const c10::optional<Tensor>& theta, Tensor X, int64_t aug_seed,
-                   const c10::optional<Tensor>& step) {
+                   const c10::optional<Tensor>& step, bool spack) {
   TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kByte && x.is_contiguous() && x.dim() == 4 && x.size(3) == 3, "x must be uint8 [B,H,W,3]");
   chk_bf16(X, "X");
   const int64_t B = x.size(0), H = x.size(1), W = x.size(2);
@@ -124,7 +126,7 @@ void preprocess_u8(const Tensor& x, const c10::optional<Tensor>& theta, Tensor X
     TORCH_CHECK(step->is_cuda() && step->scalar_type() == at::kLong && step->numel() == 1, "step must be a CUDA int64 scalar tensor");
     sp = step->data_ptr<int64_t>();
   }
-  hefl::nn::preprocess_u8(x.data_ptr<uint8_t>(), th, X.data_ptr(), (int)B, (int)H, (int)W, (uint64_t)aug_seed, sp, cur());
+  hefl::nn::preprocess_u8(x.data_ptr<uint8_t>(), th, X.data_ptr(), (int)B, (int)H, (int)W, (uint64_t)aug_seed, sp, spack ? 1 : 0, cur());
 }
 
 void unpool_relu(const Tensor& g, const Tensor& amax, const Tensor& ypool, Tensor dY, int64_t B, int64_t H,
@@ -265,12 +267,13 @@ hefl::nn::ConvLayerTable table_from(const Tensor& t) {
 
 // l0/l1: layer range [l0, l1) (l1 = -1: all layers) so the update of the layers whose gradients are final can
 // run on a side stream under the last weight-gradient kernel.
-void conv_weight_relayout(const Tensor& shadow, const Tensor& table, Tensor Wf, Tensor Wd, int64_t l0, int64_t l1) {
+void conv_weight_relayout(const Tensor& shadow, const Tensor& table, Tensor Wf, Tensor Wd, int64_t l0, int64_t l1,
+                          bool spack0) {
   chk_bf16(shadow, "shadow"); chk_bf16(Wf, "Wf"); chk_bf16(Wd, "Wd");
   const auto t = table_from(table);
   if (l1 < 0) l1 = t.n;
   TORCH_CHECK(0 <= l0 && l1 <= t.n, "layer range");
-  hefl::nn::conv_weight_relayout(shadow.data_ptr(), t, Wf.data_ptr(), Wd.data_ptr(), (int)l0, (int)l1, cur());
+  hefl::nn::conv_weight_relayout(shadow.data_ptr(), t, Wf.data_ptr(), Wd.data_ptr(), (int)l0, (int)l1, spack0 ? 1 : 0, cur());
 }
 
 void conv_grad_finalize(Tensor dW32, const Tensor& table, Tensor grad, int64_t l0, int64_t l1) {
@@ -286,10 +289,10 @@ void conv_grad_finalize(Tensor dW32, const Tensor& table, Tensor grad, int64_t l
 TORCH_LIBRARY_FRAGMENT(hefl, m) {
   m.def("adam_step_(Tensor(a!) p, Tensor(b!) g, Tensor(c!) m, Tensor(d!) v, Tensor? shadow, Tensor step, Tensor? lr_scale, float lr, float decay, float beta1, float beta2, float eps) -> ()", &adam_step_);
   m.def("gather_h2d_(Tensor(a!) dst, Tensor src, Tensor indices) -> ()", &gather_h2d_);
-  m.def("conv_fwd_pool(Tensor X, Tensor Wf, Tensor bias, Tensor(a!) out, Tensor(b!)? argmax, int B, int H, int W, int CK, int CO) -> ()", &conv_fwd_pool);
+  m.def("conv_fwd_pool(Tensor X, Tensor Wf, Tensor bias, Tensor(a!) out, Tensor(b!)? argmax, int B, int H, int W, int CK, int CO, bool spack=False) -> ()", &conv_fwd_pool);
   m.def("conv_dgrad(Tensor dY, Tensor Wd, Tensor(a!) dX, int B, int H, int W, int CK, int CO) -> ()", &conv_dgrad);
   m.def("conv_wgrad(Tensor X, Tensor DY, Tensor(a!) dW32, int B, int H, int W, int CK, int Co) -> ()", &conv_wgrad);
-  m.def("preprocess_u8(Tensor x, Tensor? theta, Tensor(a!) X, int aug_seed, Tensor? step) -> ()", &preprocess_u8);
+  m.def("preprocess_u8(Tensor x, Tensor? theta, Tensor(a!) X, int aug_seed, Tensor? step, bool spack=False) -> ()", &preprocess_u8);
   m.def("unpool_relu(Tensor g, Tensor amax, Tensor ypool, Tensor(a!) dY, int B, int H, int W, int Co) -> ()", &unpool_relu);
   m.def("head_forward_backward(Tensor feat, Tensor flat, Tensor(a!) grad, int[] offs, Tensor y, Tensor(b!) dfeat, Tensor(c!) h1_buf, Tensor(d!) dh1_buf, Tensor(e!) out, Tensor(f!)? step, int B, int F, int H1, int H2, int C, bool train) -> ()", &head_forward_backward);
   m.def("fused_update(Tensor(a!) dW32, Tensor table, Tensor(b!) flat, Tensor(c!) grad, Tensor(d!) m, Tensor(e!) v, Tensor(f!) shadow, Tensor(g!) Wf, Tensor(h!) Wd, Tensor step, Tensor? lr_scale, float lr, float decay, float beta1, float beta2, float eps, int dense_off, int n_trainable) -> ()", &fused_update);
@@ -302,6 +305,6 @@ TORCH_LIBRARY_FRAGMENT(hefl, m) {
   m.def("avgpool_forward(Tensor x, Tensor(a!) out, int B, int HW, int C) -> ()", &avgpool_forward);
   m.def("avgpool_backward(Tensor dout, Tensor(a!) dx, int B, int HW, int C) -> ()", &avgpool_backward);
   m.def("umma_shift_probe(Tensor A, Tensor Bm, int CK, int shift_rows, int mode) -> Tensor", &umma_shift_probe);
-  m.def("conv_weight_relayout(Tensor shadow, Tensor table, Tensor(a!) Wf, Tensor(b!) Wd, int l0=0, int l1=-1) -> ()", &conv_weight_relayout);
+  m.def("conv_weight_relayout(Tensor shadow, Tensor table, Tensor(a!) Wf, Tensor(b!) Wd, int l0=0, int l1=-1, bool spack0=False) -> ()", &conv_weight_relayout);
   m.def("conv_grad_finalize(Tensor(a!) dW32, Tensor table, Tensor(b!) grad, int l0=0, int l1=-1) -> ()", &conv_grad_finalize);
 }

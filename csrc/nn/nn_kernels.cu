@@ -62,10 +62,9 @@ namespace nn {
 // align_corners=False).
 __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ x, const float* __restrict__ theta,
                                      __nv_bfloat16* __restrict__ X, int B, int H, int W, uint64_t aug_seed,
-                                     const int64_t* __restrict__ step) {
+                                     const int64_t* __restrict__ step, int spack) {
   pdl_prologue();
   const int b = blockIdx.y;
-  const int HW = H * W;
   float tl[6];
   bool warp_img = theta != nullptr;
   if (theta) {
@@ -85,14 +84,23 @@ __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ x, const float*
     tl[3] = 0.f; tl[4] = cosf(sh) * zy; tl[5] = 0.f;
     warp_img = true;
   }
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
-    const int w = p % W;
-    const int h = p / W;
-    const int64_t m = (int64_t)b * HW + p;
+  // One warp = one run of consecutive pixels of an image row. With `spack` (s-packed layer-1 input: channels
+  // 0-2 = this pixel, 3-5 = pixel w+1, 6-8 = pixel w+2, so the three horizontal filter taps become part of the
+  // GEMM K dimension) a warp stores 30 pixels and lanes 30/31 only feed their values to the shuffles.
+  const int lane = threadIdx.x & 31;
+  const int PW = spack ? 30 : 32;
+  const int chunks = (W + PW - 1) / PW;
+  const int tasks = H * chunks;
+  const int wpb = blockDim.x >> 5;
+  const uint8_t* img = x + (int64_t)b * H * W * 3;
+  for (int task = blockIdx.x * wpb + (threadIdx.x >> 5); task < tasks; task += gridDim.x * wpb) {
+    const int h = task / chunks;
+    const int w = (task - h * chunks) * PW + lane;
+    const int wc = w < W ? w : W - 1;
     float c[3];
     if (warp_img) {
       const float* t = tl;
-      const float xn = (2.f * w + 1.f) / W - 1.f, yn = (2.f * h + 1.f) / H - 1.f;
+      const float xn = (2.f * wc + 1.f) / W - 1.f, yn = (2.f * h + 1.f) / H - 1.f;
       const float sx = t[0] * xn + t[1] * yn + t[2], sy = t[3] * xn + t[4] * yn + t[5];
       float ix = ((sx + 1.f) * W - 1.f) * 0.5f, iy = ((sy + 1.f) * H - 1.f) * 0.5f;
       ix = fminf(fmaxf(ix, 0.f), (float)(W - 1));
@@ -100,7 +108,6 @@ __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ x, const float*
       const int x0 = (int)floorf(ix), y0 = (int)floorf(iy);
       const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
       const float fx = ix - x0, fy = iy - y0;
-      const uint8_t* img = x + (int64_t)b * H * W * 3;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const float v00 = img[((int64_t)y0 * W + x0) * 3 + k], v01 = img[((int64_t)y0 * W + x1) * 3 + k];
@@ -109,23 +116,35 @@ __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ x, const float*
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) c[k] = (float)x[m * 3 + k] * (1.f / 255.f);
+      for (int k = 0; k < 3; ++k) c[k] = (float)img[((int64_t)h * W + wc) * 3 + k] * (1.f / 255.f);
     }
-    const uint32_t b0 = __bfloat16_as_ushort(__float2bfloat16(c[0]));
-    const uint32_t b1 = __bfloat16_as_ushort(__float2bfloat16(c[1]));
-    const uint32_t b2 = __bfloat16_as_ushort(__float2bfloat16(c[2]));
-    uint4* dst = reinterpret_cast<uint4*>(X + m * 16);
-    dst[0] = make_uint4(b0 | (b1 << 16), b2, 0u, 0u);
-    dst[1] = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t p01 = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(c[0])) |
+                   ((uint32_t)__bfloat16_as_ushort(__float2bfloat16(c[1])) << 16);
+    uint32_t p2 = __bfloat16_as_ushort(__float2bfloat16(c[2]));
+    if (w >= W) { p01 = 0u; p2 = 0u; }                       // past the row end: zero neighbours
+    const uint32_t n1_01 = __shfl_down_sync(0xffffffffu, p01, 1), n1_2 = __shfl_down_sync(0xffffffffu, p2, 1);
+    const uint32_t n2_01 = __shfl_down_sync(0xffffffffu, p01, 2), n2_2 = __shfl_down_sync(0xffffffffu, p2, 2);
+    if (lane < PW && w < W) {
+      uint4* dst = reinterpret_cast<uint4*>(X + ((int64_t)(b * H + h) * W + w) * 16);
+      if (spack) {
+        dst[0] = make_uint4(p01, p2 | (n1_01 << 16), (n1_01 >> 16) | (n1_2 << 16), n2_01);
+        dst[1] = make_uint4(n2_2, 0u, 0u, 0u);
+      } else {
+        dst[0] = make_uint4(p01, p2, 0u, 0u);
+        dst[1] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
   }
 }
 
 void preprocess_u8(const uint8_t* x, const float* theta, void* X, int B, int H, int W, uint64_t aug_seed,
-                   const int64_t* step, cudaStream_t st) {
-  int bx = (H * W + 255) / 256;
+                   const int64_t* step, int spack, cudaStream_t st) {
+  const int tasks = H * ((W + (spack ? 29 : 31)) / (spack ? 30 : 32));
+  int bx = (tasks + 7) / 8;
   if (bx > 64) bx = 64;
   dim3 grid(bx, B);
-  launch_pdl(preprocess_u8_kernel, dim3(grid), dim3(256), 0, st, x, theta, reinterpret_cast<__nv_bfloat16*>(X), B, H, W, aug_seed, step);
+  launch_pdl(preprocess_u8_kernel, dim3(grid), dim3(256), 0, st, x, theta, reinterpret_cast<__nv_bfloat16*>(X), B, H, W,
+             aug_seed, step, spack);
   hefl::cuda::note_launch();
 }
 
@@ -197,11 +216,22 @@ void unpool_relu(const void* g, const uint8_t* amax, const void* ypool, void* dY
 // bf16 shadow of the flat parameters ([Co][Ci][3][3] per conv) -> Wf [tap][Co][CK] (forward B
 // operand, channel-padded) and Wd [tap][Ci][Co] (dgrad B operand).
 __global__ void conv_weight_relayout_kernel(const __nv_bfloat16* __restrict__ shadow, const ConvLayerTable t,
-                                            __nv_bfloat16* __restrict__ Wf, __nv_bfloat16* __restrict__ Wd, int l0) {
+                                            __nv_bfloat16* __restrict__ Wf, __nv_bfloat16* __restrict__ Wd, int l0,
+                                            int spack0) {
   pdl_wait();   // parameter writer: no early trigger (see launch.cuh)
   const int l = blockIdx.y + l0;
   const int Ci = t.Ci[l], CK = t.CK[l], Co = t.Co[l];
   const __nv_bfloat16* w = shadow + t.w_off[l];
+  if (l == 0 && spack0) {
+    // s-packed layer 1: Wf [3 filter rows][Co][CK], k = s*Ci + ci (the input carries pixels w, w+1, w+2)
+    const int nf = 3 * Co * CK;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf; i += gridDim.x * blockDim.x) {
+      const int k = i % CK, co = (i / CK) % Co, r = i / (CK * Co);
+      const int sx = k / Ci, ci = k - sx * Ci;
+      Wf[t.wf_off[l] + i] = k < 3 * Ci ? w[(co * Ci + ci) * 9 + r * 3 + sx] : __float2bfloat16(0.f);
+    }
+    return;
+  }
   const int nf = 9 * Co * CK;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf; i += gridDim.x * blockDim.x) {
     const int ck = i % CK, co = (i / CK) % Co, tap = i / (CK * Co);
@@ -217,12 +247,12 @@ __global__ void conv_weight_relayout_kernel(const __nv_bfloat16* __restrict__ sh
 }
 
 void conv_weight_relayout(const void* shadow, const ConvLayerTable& t, void* Wf, void* Wd, int l0, int l1,
-                          cudaStream_t st) {
+                          int spack0, cudaStream_t st) {
   if (l1 <= l0) return;
   dim3 grid(32, l1 - l0);
   launch_pdl(conv_weight_relayout_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(shadow), t,
                                                     reinterpret_cast<__nv_bfloat16*>(Wf),
-                                                    reinterpret_cast<__nv_bfloat16*>(Wd), l0);
+                                                    reinterpret_cast<__nv_bfloat16*>(Wd), l0, spack0);
   hefl::cuda::note_launch();
 }
 

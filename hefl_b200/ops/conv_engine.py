@@ -65,6 +65,9 @@ class MedCNNEngine:
             self.Co.append(co)
             h = (h - 2) // 2
         self.H.append(h)                 # feature map side
+        # layer-1 input carries pixels (w, w+1, w+2) in its 16 channels: 3 tap-GEMMs instead of 9 (conv_tcgen05.cu TS=1)
+        self.spack0 = (os.environ.get("HEFL_SPACK0", "1") != "0" and self.Ci[0] == 3 and self.CK[0] == 16
+                       and self.Co[0] == 32)
         # layer-1 weight gradient by gather from the pooled gradient (csrc/nn/wgrad_gather.cu)
         self.gather_wgrad0 = (os.environ.get("HEFL_GATHER_WGRAD0", "1") != "0" and self.Co[0] == 32
                               and self.CK[0] == 16 and self.H[0] <= 256)
@@ -136,7 +139,7 @@ class MedCNNEngine:
     # ------------------------------------------------------------------ weights
     def after_update(self) -> None:
         """Called after Adam wrote the bf16 shadow: rebuild the tensor-core weight layouts."""
-        self.ops.conv_weight_relayout(self.shadow, self.table, self.Wf, self.Wd)
+        self.ops.conv_weight_relayout(self.shadow, self.table, self.Wf, self.Wd, 0, -1, self.spack0)
 
     def after_restore(self) -> None:
         self.shadow.copy_(self.pack.trainable())
@@ -175,14 +178,15 @@ class MedCNNEngine:
         if train and augment:
             seed = (self.aug_seed + 0x9E3779B97F4A7C15 * (self.prep_count + 1)) & 0x7FFFFFFFFFFFFFFF or 1
             self.prep_count += 1
-        self.ops.preprocess_u8(x_u8, None, self.X0[slot], seed, None)
+        self.ops.preprocess_u8(x_u8, None, self.X0[slot], seed, None, self.spack0)
 
     def forward_convs(self, slot: int, train: bool) -> torch.Tensor:
         x = self.X0[slot]
         for l in range(self.n):
             h = self.H[l]
             self.ops.conv_fwd_pool(x, self._wf(l), self.bias[l], self.X[l + 1],
-                                   self.amax[l] if train else None, self.B, h, h, self.CK[l], self.Co[l])
+                                   self.amax[l] if train else None, self.B, h, h, self.CK[l], self.Co[l],
+                                   self.spack0 and l == 0)
             x = self.X[l + 1]
         return self.X[self.n]
 
@@ -264,7 +268,7 @@ class MedCNNEngine:
         elif split:
             self.ops.conv_grad_finalize(self.dW32, self.table, self.pack.grad, 0, 1)
             opt.apply(0, self.p0)
-            self.ops.conv_weight_relayout(self.shadow, self.table, self.Wf, self.Wd, 0, 1)
+            self.ops.conv_weight_relayout(self.shadow, self.table, self.Wf, self.Wd, 0, 1, self.spack0)
         else:
             opt.bump()
             self.ops.conv_grad_finalize(self.dW32, self.table, self.pack.grad)
@@ -276,6 +280,8 @@ class MedCNNEngine:
         self.ops.fused_update(self.dW32, self.table, self.pack.flat, self.pack.grad, m, v, self.shadow, self.Wf, self.Wd,
                               step, lr_scale, cfg.lr, cfg.lr_decay, 0.9, 0.999, 1e-7, self.dense_off,
                               self.pack.n_trainable)
+        if self.spack0:
+            self.ops.conv_weight_relayout(self.shadow, self.table, self.Wf, self.Wd, 0, 1, True)
 
     def eval_step(self, x_u8: torch.Tensor, y: torch.Tensor, out: torch.Tensor) -> None:
         self.preprocess(x_u8, 0, False, False)

@@ -135,6 +135,44 @@ def test_preprocess_matches_grid_sample():
     assert (X.view(B, H, H, 16)[..., :3].float() - ref).abs().max() < 1e-2
 
 
+@pytest.mark.parametrize("H", [256, 70])
+def test_spack_first_layer_matches_torch(H):
+    """s-packed first layer: preprocess_u8(spack) writes pixels (w, w+1, w+2) into the 16 channels and the
+    forward kernel runs 3 tap-GEMMs instead of 9; result == conv -> ReLU -> max-pool of the plain image."""
+    B, Ci, Co = 2, 3, 32
+    g = torch.Generator(device="cuda").manual_seed(31)
+    x = torch.randint(0, 256, (B, H, H, 3), dtype=torch.uint8, device="cuda", generator=g)
+    w = _bf(torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) * 0.3)
+    bias = torch.randn(Co, device="cuda", generator=g) * 0.1
+    P = B * H * H
+    X = torch.zeros(P, 16, dtype=torch.bfloat16, device="cuda")
+    ops.preprocess_u8(x, None, X, 0, None, True)
+    xv = X.view(B, H, H, 16).float()
+    ref_px = _bf(x.float() / 255.0).float()
+    assert torch.equal(xv[..., 0:3], ref_px)
+    assert torch.equal(xv[:, :, :-1, 3:6], ref_px[:, :, 1:]) and torch.equal(xv[:, :, :-2, 6:9], ref_px[:, :, 2:])
+    assert float(xv[..., 9:].abs().max()) == 0.0
+    # packed weights: [r][co][k = s*3 + ci]
+    Wp = torch.zeros(3, Co, 16, dtype=torch.bfloat16, device="cuda")
+    Wp[:, :, :9] = w.permute(2, 0, 3, 1).reshape(3, Co, 9).to(torch.bfloat16)
+    Hp = (H - 2) // 2
+    out = torch.zeros(B * Hp * Hp, Co, dtype=torch.bfloat16, device="cuda")
+    amax = torch.zeros(B * Hp * Hp, Co, dtype=torch.uint8, device="cuda")
+    ops.conv_fwd_pool(X, Wp.view(-1), bias, out, amax, B, H, H, 16, Co, True)
+    ref = F.max_pool2d(F.relu(F.conv2d(ref_px.permute(0, 3, 1, 2), w.float(), bias)), 2)
+    got = out.view(B, Hp, Hp, Co).permute(0, 3, 1, 2).float()
+    assert (got - ref).abs().max() <= 2.0 ** -7 * ref.abs().max() + 1e-3
+    # same pooled output and arg-max as the 9-tap kernel on the plain layout
+    X9 = torch.zeros(P, 16, dtype=torch.bfloat16, device="cuda")
+    ops.preprocess_u8(x, None, X9, 0, None, False)
+    W9 = torch.zeros(9, Co, 16, dtype=torch.bfloat16, device="cuda")
+    W9[:, :, :Ci] = w.permute(2, 3, 0, 1).reshape(9, Co, Ci).to(torch.bfloat16)
+    out9 = torch.zeros_like(out); amax9 = torch.zeros_like(amax)
+    ops.conv_fwd_pool(X9, W9.view(-1), bias, out9, amax9, B, H, H, 16, Co, False)
+    assert (out.float() - out9.float()).abs().max() <= 2.0 ** -7 * ref.abs().max() + 1e-3
+    assert ((amax & 4) == (amax9 & 4)).float().mean() > 0.999
+
+
 @pytest.mark.parametrize("cluster", [1, 0])
 @pytest.mark.parametrize("B,C,train", [(32, 2, True), (8, 2, True), (32, 3, True), (16, 2, False)])
 def test_head_matches_autograd(cluster, B, C, train):
@@ -284,6 +322,8 @@ def test_fused_update_matches_separate_path():
         tr = LocalTrainer(model, pack, cfg, dev, backend="tcgen05", use_graph=False, augment=False)
         tr.engine.fused_step = fused
         tr.engine.two_streams = fused
+        tr.engine.spack0 = False          # the one-launch update writes the plain 9-tap layer-1 layout
+        tr.engine.after_restore()
         g = torch.Generator(device="cuda").manual_seed(3)
         x = torch.randint(0, 256, (8, 256, 256, 3), dtype=torch.uint8, device="cuda", generator=g)
         y = torch.randint(0, 2, (8,), device="cuda", generator=g)

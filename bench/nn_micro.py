@@ -40,16 +40,19 @@ def main():
     res = {}
     th = eng._make_theta()
     res["make_theta(torch)"] = timeit(lambda: eng._make_theta())
-    res["preprocess"] = timeit(lambda: ops.preprocess_u8(x, None, eng.X[0], 99, None))
+    res["preprocess"] = timeit(lambda: ops.preprocess_u8(x, None, eng.X[0], 99, None, eng.spack0))
     for l in range(eng.n):
         h = eng.H[l]
-        res[f"fwd{l}"] = timeit(lambda l=l, h=h: ops.conv_fwd_pool(eng.X[l], eng._wf(l), eng.bias[l], eng.X[l + 1], eng.amax[l], B, h, h, eng.CK[l], eng.Co[l]))
+        res[f"fwd{l}"] = timeit(lambda l=l, h=h: ops.conv_fwd_pool(eng.X[l], eng._wf(l), eng.bias[l], eng.X[l + 1], eng.amax[l], B, h, h, eng.CK[l], eng.Co[l], eng.spack0 and l == 0))
     g = torch.randn(B, 512, device="cuda").to(torch.bfloat16).view_as(eng.X[eng.n]).contiguous()
     for l in range(eng.n - 1, -1, -1):
         h = eng.H[l]
         gin = g if l == eng.n - 1 else eng.gX[l + 1]
+        if l == 0:
+            res["wgrad0(gather from pooled grad)"] = timeit(lambda: ops.wgrad0_gather(eng._x0_bufs[0], gin, eng.amax[0], eng._dw(0), B, h, h))
+            eng.dY[0] = torch.zeros(eng.P[0], eng.Co[0], dtype=torch.bfloat16, device="cuda")
         res[f"unpool{l}"] = timeit(lambda l=l, h=h, gin=gin: ops.unpool_relu(gin, eng.amax[l], eng.X[l + 1], eng.dY[l], B, h, h, eng.Co[l]))
-        res[f"wgrad{l}"] = timeit(lambda l=l, h=h: ops.conv_wgrad(eng.X[l], eng.dY[l], eng._dw(l), B, h, h, eng.CK[l], eng.Co[l]))
+        res[f"wgrad{l}(tcgen05)"] = timeit(lambda l=l, h=h: ops.conv_wgrad(eng.X[l], eng.dY[l], eng._dw(l), B, h, h, eng.CK[l], eng.Co[l]))
         if l > 0:
             res[f"dgrad{l}"] = timeit(lambda l=l, h=h: ops.conv_dgrad(eng.dY[l], eng._wd(l), eng.gX[l], B, h, h, eng.Co[l], eng.Ci[l]))
     res["finalize"] = timeit(lambda: ops.conv_grad_finalize(eng.dW32, eng.table, pack.grad))
@@ -62,14 +65,20 @@ def main():
         loss.backward()
         return feat.grad.to(torch.bfloat16)
     res["head(torch fwd+bwd)"] = timeit(head)
-    res["head(fused kernels)"] = timeit(lambda: ops.head_forward_backward(eng.X[eng.n], pack.flat, pack.grad, eng.head_offs, y, eng.dfeat, eng.h1_buf, eng.dh1_buf, out, None, B, eng.F, eng.H1, eng.H2, eng.C, True))
+    head_call = lambda: ops.head_forward_backward(eng.X[eng.n], pack.flat, pack.grad, eng.head_offs, y, eng.dfeat, eng.h1_buf, eng.dh1_buf, out, None, B, eng.F, eng.H1, eng.H2, eng.C, True)
+    ops.set_head_cluster(0)
+    res["head(4 kernels)"] = timeit(head_call)
+    ops.set_head_cluster(1)
+    res["head(cluster kernel)"] = timeit(head_call)
     m = torch.zeros_like(pack.grad); v = torch.zeros_like(pack.grad); st = torch.ones(1, dtype=torch.int64, device="cuda")
-    res["fused_update"] = timeit(lambda: ops.fused_update(eng.dW32, eng.table, pack.flat, pack.grad, m, v, eng.shadow, eng.Wf, eng.Wd, st, None, 1e-3, 1e-4, 0.9, 0.999, 1e-7, eng.dense_off, pack.n_trainable))
+    res["fused_update(legacy, off)"] = timeit(lambda: ops.fused_update(eng.dW32, eng.table, pack.flat, pack.grad, m, v, eng.shadow, eng.Wf, eng.Wd, st, None, 1e-3, 1e-4, 0.9, 0.999, 1e-7, eng.dense_off, pack.n_trainable))
     res["adam"] = timeit(lambda: ops.adam_step_(pack.trainable(), pack.grad, m, v, eng.shadow, st, None, 1e-3, 1e-4, 0.9, 0.999, 1e-7))
     eng.step_ref = st
+    from hefl_b200.fl.trainer import LocalTrainer
+    tr = LocalTrainer(model, pack, cfg, dev, backend="tcgen05", use_graph=False)
+    eng = tr.engine
     def full_step():
-        eng.train_step(x, y, out, augment=True)
-        eng.fused_update(m, v, st, None, cfg)
+        tr.train_step(x, y)
     res["train_step(eager)"] = timeit(full_step, iters=5)
     # whole step as a CUDA graph
     side = torch.cuda.Stream()
@@ -80,7 +89,8 @@ def main():
     with torch.cuda.graph(gph):
         full_step()
     res["train_step(graph)"] = timeit(lambda: gph.replay(), iters=10)
-    tot = sum(v for k, v in res.items() if not k.startswith("train_step") and not k.startswith("head(torch") and not k.startswith("make_theta"))
+    skip = ("train_step", "head(torch", "head(4", "make_theta", "fused_update", "unpool0", "wgrad0(tcgen05)")
+    tot = sum(v for k, v in res.items() if not k.startswith(skip))
     for k, v in res.items():
         print(f"{k:24s} {v:9.1f} us")
     print(f"{'sum of parts':24s} {tot:9.1f} us")

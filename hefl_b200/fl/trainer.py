@@ -83,6 +83,7 @@ class LocalTrainer:
             self.prep_stream = torch.cuda.Stream(device)
             self._slot_ready = [torch.cuda.Event() for _ in range(2)]
             self._slot_free = [torch.cuda.Event() for _ in range(2)]
+            self._pre = None         # (feeder, train, iterator, slot) of a first batch staged ahead of its pass
 
     # ------------------------------------------------------------------ one step (eager)
     def _prep(self, x_u8: torch.Tensor, train: bool) -> torch.Tensor:
@@ -240,12 +241,14 @@ class LocalTrainer:
             self._eval_eager(x_u8, y)
         return self.out_eval
 
-    def _run_epoch(self, feeder, train: bool, stats: torch.Tensor) -> None:
+    def _run_epoch(self, feeder, train: bool, stats: torch.Tensor, nxt=None) -> None:
         """One pass over ``feeder``; per-step [loss, ncorrect] land in ``stats`` (pinned host rows).
 
         tcgen05 engine + CUDA graphs: software pipeline over batches — batch i+1 is fetched (H2D or
         on-device gather) and pre-processed into the other X0 slot on ``prep_stream`` while the captured
-        graph of step i runs on the main stream; events hand the slots back and forth."""
+        graph of step i runs on the main stream; events hand the slots back and forth. ``nxt`` =
+        (feeder, train) of the pass that follows: its first batch is staged under this pass's last
+        step, so consecutive passes (train -> validation -> next epoch) have no pipeline-fill bubble."""
         if self.engine is None or not self.use_graph:
             for i, (x, y) in enumerate(feeder.epoch()):
                 out = self.train_step(x, y) if train else self.eval_step(x, y)
@@ -254,28 +257,36 @@ class LocalTrainer:
         if not self._graphs:
             self._capture()
         main, prep, sst = torch.cuda.current_stream(self.device), self.prep_stream, self.stats_stream
-        prep.wait_stream(main)
-        for ev in self._slot_free:
-            ev.record(main)
-        for ev in self._stats_done:
-            ev.record(main)
-        it = iter(feeder.epoch())
         n = feeder.steps
         outs = self.out_train2 if train else self.out_eval2
 
-        def stage(slot: int) -> None:
+        def stage(it, slot: int, tr: bool) -> None:
             with torch.cuda.stream(prep):
                 prep.wait_event(self._slot_free[slot])        # the graph that last read this slot is done
                 x, y = next(it)                               # feeder work (gather / wait for H2D) on prep
-                self.engine.preprocess(x, slot, train, self.augment and train)
+                self.engine.preprocess(x, slot, tr, self.augment and tr)
                 self.static_y2[slot].copy_(y, non_blocking=True)
                 self._slot_ready[slot].record(prep)
 
-        stage(0)
+        pre, self._pre = self._pre, None
+        if pre is not None and pre[0] is feeder and pre[1] == train:
+            it, s0 = pre[2], pre[3]                           # batch 0 was staged by the previous pass
+        else:
+            if pre is not None:
+                pre[2].close()
+            prep.wait_stream(main)
+            for ev in self._slot_free + self._stats_done:
+                ev.record(main)
+            it, s0 = iter(feeder.epoch()), 0
+            stage(it, 0, train)
         for i in range(n):
-            slot = i & 1
+            slot = (s0 + i) & 1
             if i + 1 < n:
-                stage(slot ^ 1)
+                stage(it, slot ^ 1, train)
+            elif nxt is not None and nxt[0] is not None and nxt[0].steps > 0:
+                nit = iter(nxt[0].epoch())
+                stage(nit, slot ^ 1, nxt[1])
+                self._pre = (nxt[0], nxt[1], nit, slot ^ 1)
             main.wait_event(self._slot_ready[slot])
             main.wait_event(self._stats_done[slot])           # result buffer of this slot has been read back
             self._graphs[(train, slot)].replay()
@@ -288,8 +299,13 @@ class LocalTrainer:
         with torch.cuda.stream(prep):
             for _ in it:                                      # let the feeder finish its bookkeeping
                 pass
-        main.wait_stream(prep)
         main.wait_stream(sst)
+
+    def _drop_prefetch(self) -> None:
+        pre, self._pre = getattr(self, "_pre", None), None
+        if pre is not None:
+            pre[2].close()
+            torch.cuda.current_stream(self.device).wait_stream(self.prep_stream)
 
     def fit(self, train: BatchFeeder, val: Optional[BatchFeeder], epochs: int,
             early_stopping: Optional[int] = 5, restore_best: bool = True,
@@ -308,12 +324,14 @@ class LocalTrainer:
         for ep in range(epochs):
             self.model.train()
             ts = ts_all[: train.steps]
-            self._run_epoch(train, True, ts)
+            has_val = val is not None and val.steps > 0
+            again = (train, True) if ep + 1 < epochs else None
+            self._run_epoch(train, True, ts, nxt=(val, False) if has_val else again)
             vs = None
-            if val is not None and val.steps > 0:
+            if has_val:
                 self.model.eval()
                 vs = vs_all[:nval]
-                self._run_epoch(val, False, vs)
+                self._run_epoch(val, False, vs, nxt=again)
             if self.cuda:
                 torch.cuda.current_stream(self.device).synchronize()
             loss = float(ts[:, 0].mean())
@@ -348,6 +366,8 @@ class LocalTrainer:
                         if self.engine is not None:
                             self.engine.after_restore()
                     break
+        if self.engine is not None:
+            self._drop_prefetch()
         return hist
 
     def _stat_buffers(self, ntrain: int, nval: int):

@@ -54,6 +54,7 @@ class FLConfig:
     clients: int = 2
     rounds: int = 1
     compat_sequential_clients: bool = False   # reproduce quirk Q1 (FLPyfhelin.py:180-193)
+    debug_poison: bool = False                # overwrite ciphertext / scratch buffers with a poison pattern between rounds
     # HE
     he_preset: str = "n4096_l3"
     packing: str = "slots"            # slots (canonical embedding, N/2 per ct) | coeff (N per ct)

@@ -158,6 +158,8 @@ class FederatedRunner:
             ct = self.encrypt_update()
             agg = self.aggregate(ct)
             self.decrypt_apply(agg)
+        if self.cfg.debug_poison:
+            self.poison_buffers()
         times = self.timer.resolve()
         if hasattr(self.transport, "check_status"):
             self.transport.check_status()
@@ -169,6 +171,20 @@ class FederatedRunner:
         self.history.append(rec)
         self.round += 1
         return rec
+
+    POISON = 0x7FF8DEADBEEF7FF8          # > every q_l: a stale word can never pass for a residue
+
+    def poison_buffers(self) -> None:
+        """Debug mode (``debug_poison`` / HEFL_DEBUG_POISON=1): after the round's result is
+        installed, every buffer that carried ciphertext words is overwritten, so a later round that reads
+        something it did not write this round (stale tile, missed barrier) decodes to garbage and trips
+        ``guard_finite`` / the plaintext cross-check instead of silently reusing last round's data."""
+        buf = self.transport.buffer(self.ct_numel)
+        buf.fill_(self.POISON)
+        out = getattr(self.transport, "out", None)
+        if isinstance(out, torch.Tensor):
+            out.fill_(self.POISON)
+        self.poisoned = getattr(self, "poisoned", 0) + 1
 
     def run(self, rounds: Optional[int] = None) -> List[Dict]:
         out = []

@@ -64,3 +64,23 @@ def test_keras_dict_roundtrip():
     p.flat.zero_()
     p.from_keras_dict(d)
     assert torch.equal(p.flat, before)
+
+
+def test_debug_poison_between_rounds_keeps_results_identical():
+    """Poisoning the ciphertext buffers after every round (SURVEY.md §5.2 debug mode) must not change
+    any result: every round rewrites all the words it reads."""
+    import torch
+    from hefl_b200.config import FLConfig
+    from hefl_b200.fl import FederatedRunner
+
+    def run(poison):
+        cfg = _cfg(local_epochs=1, steps_per_epoch=2, clients=1, seed=3, debug_poison=poison)
+        r = FederatedRunner(cfg, device=torch.device("cpu"))
+        for _ in range(2):
+            r.run_round(check=True)
+        return r.pack.flat.clone(), getattr(r, "poisoned", 0), r
+
+    a, na, _ = run(False)
+    b, nb, rb = run(True)
+    assert na == 0 and nb == 2
+    assert torch.equal(a, b)

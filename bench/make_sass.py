@@ -12,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "hefl_b200", "_obj")
 OUT = os.path.join(ROOT, "profiles", "sass")
 KEY = re.compile(r"\b(UTCHMMA|UTCQMMA|UTMALDG|UTMASTG|UBLKCP|LDTM|STTM|UTCBAR|UTCATOMSWS|SYNCS|MULTIMEM|ATOMG|ATOM|RED|LDGSTS|"
-                 r"HMMA|IMAD|LDS|STS|LDG|STG|SHFL|BAR|MEMBAR|ERRBAR|CCTL|ELECT|R2UR|UIADD3|UMOV|FFMA|DFMA|DADD|DMUL)\b")
+                 r"HMMA|IMAD|LDS|STS|LDG|STG|SHFL|BAR|MEMBAR|ERRBAR|CCTL|ELECT|R2UR|UIADD3|UMOV|FFMA|FFMA2|FHFMA|UCGABAR_ARV|UCGABAR_WAIT|"
+                 r"ACQBULK|DFMA|DADD|DMUL)\b")
 
 
 def demangle(names):

@@ -306,17 +306,19 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int tw = rem - hp * a.tiles_w;
         const int col = tw * 128 + qd * 32 + lane;           // conv-output column of this thread
         const int wp = col >> 1;
-        const bool writer = ((lane & 1) == 0) && wp < a.Wp;
+        const bool writer = wp < a.Wp;
+        const bool odd = (lane & 1) != 0;
 #pragma unroll 1
         for (int ch = grp; ch < ((a.dbg & 4) ? 0 : CO / 8); ch += 2) {
           float v0[8], v1[8];
           tmem_ld8_nowait(tmem_base + lane_base + (tb * 2 + 0) * CO + ch * 8, v0);
           tmem_ld8_nowait(tmem_base + lane_base + (tb * 2 + 1) * CO + ch * 8, v1);
-          const float4 bA = __ldg(reinterpret_cast<const float4*>(a.bias + ch * 8));
-          const float4 bB = __ldg(reinterpret_cast<const float4*>(a.bias + ch * 8 + 4));
-          const float bias8[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+          // the two lanes of a window split the 8 channels: even lane -> 0..3, odd lane -> 4..7 (the epilogue is
+          // issue-bound — ncu: 64 % issue active, 5 % tensor pipe — so no lane may do redundant work)
+          const float4 bq = __ldg(reinterpret_cast<const float4*>(a.bias + ch * 8 + (odd ? 4 : 0)));
+          const float bias4[4] = {bq.x, bq.y, bq.z, bq.w};
           tmem_ld_wait();
-          // max over the 2x2 window on the raw accumulators (bias + ReLU commute with max)
+          // max over the two image rows on the raw accumulators (bias + ReLU commute with max)
           uint32_t vbits = 0;                                 // 1 = lower image row wins
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -325,28 +327,27 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             vbits |= lw ? (1u << c) : 0u;
           }
           const uint32_t pvbits = __shfl_xor_sync(0xffffffffu, vbits, 1);
-          uint32_t packed[4];
-          uint32_t idx4[2] = {0u, 0u};
+          const uint32_t mb = (vbits >> (odd ? 4 : 0)) & 15u;   // row bits of my column, my 4 channels
+          const uint32_t pb = (pvbits >> (odd ? 4 : 0)) & 15u;  // ... of the partner's column
+          float x[4];
+          uint32_t idx = 0u;
 #pragma unroll
-          for (int c = 0; c < 8; c += 2) {
-            float x[2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const float mine = v0[c + j];
-              const float o = __shfl_xor_sync(0xffffffffu, mine, 1);
-              const bool rw = o > mine;
-              const uint32_t id = rw ? (((pvbits >> (c + j)) & 1u) * 2u + 1u) : (((vbits >> (c + j)) & 1u) * 2u);
-              const float y = (rw ? o : mine) + bias8[c + j];
-              // bits 0-1: arg-max position (row*2 + col) in the window, bit 2: unit active (ReLU mask)
-              idx4[(c + j) >> 2] |= (id | (y > 0.f ? 4u : 0u)) << (((c + j) & 3) * 8);
-              x[j] = y > 0.f ? y : 0.f;
-            }
-            packed[c >> 1] = pack_bf16x2(x[0], x[1]);
+          for (int i = 0; i < 4; ++i) {
+            const float keep = odd ? v0[4 + i] : v0[i];
+            const float send = odd ? v0[i] : v0[4 + i];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            const float left = odd ? recv : keep, right = odd ? keep : recv;
+            const bool rw = right > left;                       // right column wins only if strictly greater
+            const uint32_t rowbit = ((rw != odd) ? (pb >> i) : (mb >> i)) & 1u;
+            const float y = (rw ? right : left) + bias4[i];
+            // bits 0-1: arg-max position (row*2 + col) in the window, bit 2: unit active (ReLU mask)
+            idx |= ((rowbit << 1) | (rw ? 1u : 0u) | (y > 0.f ? 4u : 0u)) << (i * 8);
+            x[i] = y > 0.f ? y : 0.f;
           }
           if (writer) {
-            const size_t o = ((size_t)(b * a.Hp + hp) * a.Wp + wp) * CO + ch * 8;
-            *reinterpret_cast<uint4*>(a.out + o) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            if (a.argmax) *reinterpret_cast<uint2*>(a.argmax + o) = make_uint2(idx4[0], idx4[1]);
+            const size_t o = ((size_t)(b * a.Hp + hp) * a.Wp + wp) * CO + ch * 8 + (odd ? 4 : 0);
+            *reinterpret_cast<uint2*>(a.out + o) = make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
+            if (a.argmax) *reinterpret_cast<uint32_t*>(a.argmax + o) = idx;
           }
         }
       } else {

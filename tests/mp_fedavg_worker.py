@@ -33,12 +33,12 @@ def main():
     if args.model == "medcnn":
         cfg = FLConfig(model="medcnn", local_epochs=1, steps_per_epoch=2, val_steps=1, clients=world,
                        nn_backend="tcgen05" if gpu else "cudnn", transport=args.transport or "fused",
-                       device="cuda" if gpu else "cpu")
+                       device="cuda" if gpu else "cpu", debug_poison=True)
     else:
         cfg = FLConfig(model="cnn2", image_size=28, in_channels=1, num_classes=10, batch_size=8, local_epochs=1,
                        steps_per_epoch=2, val_steps=1, clients=world, he_preset="n4096_l3", nn_backend="cudnn",
                        dtype="bf16" if gpu else "fp32", transport=args.transport or ("fused" if gpu else "gloo"),
-                       device="cuda" if gpu else "cpu")
+                       device="cuda" if gpu else "cpu", debug_poison=True)   # stale words would break the cross-check
     run = FederatedRunner(cfg, rank=rank, world=world, device=device)
     worst = 0.0
     for rnd in range(args.rounds):

@@ -67,6 +67,12 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
+    # stdout carries exactly ONE line (the result JSON of rank 0): anything a library prints to fd 1
+    # meanwhile (e.g. "NCCL version ..." when NCCL_DEBUG is set on the box) is routed to stderr
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -80,7 +86,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "bench.py needs a CUDA device"}))
+        os.write(result_fd, (json.dumps({"error": "bench.py needs a CUDA device"}) + "\n").encode())
         return 1
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
@@ -192,7 +198,7 @@ def main():
         if e2e is not None:
             e2e["gpu_launches"] = e2e_launches
             out["e2e"] = e2e
-        print(json.dumps(out))
+        os.write(result_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -63,6 +63,8 @@ def main():
     ap.add_argument("--nn-backend", default="auto")
     ap.add_argument("--transport", default=None)
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp8"],
+                    help="fp8: e4m3 1x1 convolutions for the ResNets (BASELINE configs[4]); the headline config is bf16")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -108,7 +110,7 @@ def main():
     transport = args.transport or ("nccl" if args.impl == "baseline" else "fused")
     cfg = FLConfig(model=args.model, he_preset=args.he_preset, local_epochs=args.local_epochs,
                    steps_per_epoch=args.steps_per_epoch, val_steps=args.val_steps, clients=world,
-                   nn_backend=nn_backend, transport=transport, device="cuda")
+                   nn_backend=nn_backend, transport=transport, device="cuda", dtype=args.dtype)
     if args.model.startswith("resnet"):
         cfg.image_size, cfg.num_classes = 224, 1000
     run = FederatedRunner(cfg, rank=rank, world=world, device=device)

@@ -42,6 +42,7 @@ void bn_backward(const void* dy, const void* x, const void* y, const float* mean
                  const float* gamma, float* sums, void* dx, void* dres, int64_t P, int C, int relu, cudaStream_t st);
 void avgpool_forward(const void* x, float* out, int B, int HW, int C, cudaStream_t st);
 void avgpool_backward(const float* dout, void* dx, int B, int HW, int C, cudaStream_t st);
+void fp8_quantize(const void* x, uint8_t* q, const float* scale, float* amax, int64_t n, cudaStream_t st);
 void umma_shift_probe(const void* A, const void* Bm, float* out, int CK, int shift_rows, int mode, cudaStream_t st);
 
 // ---- data-movement kernels around the convolutions (nn_kernels.cu) ----

@@ -230,6 +230,16 @@ void avgpool_backward(const Tensor& dout, Tensor dx, int64_t B, int64_t HW, int6
   hefl::nn::avgpool_backward(dout.data_ptr<float>(), dx.data_ptr(), (int)B, (int)HW, (int)C, cur());
 }
 
+// q = e4m3(sat(x * scale)) (q: uint8 storage, viewed as float8_e4m3fn by the caller); amax = max(amax, |x|).
+void fp8_quantize(const Tensor& x, Tensor q, const Tensor& scale, Tensor amax) {
+  chk_bf16(x, "x");
+  TORCH_CHECK(q.is_cuda() && q.is_contiguous() && q.element_size() == 1 && q.numel() == x.numel(), "q must be a 1-byte tensor like x");
+  TORCH_CHECK(x.numel() % 8 == 0, "numel must be a multiple of 8");
+  TORCH_CHECK(scale.is_cuda() && scale.scalar_type() == at::kFloat && amax.is_cuda() && amax.scalar_type() == at::kFloat, "scale / amax must be float32 CUDA scalars");
+  hefl::nn::fp8_quantize(x.data_ptr(), reinterpret_cast<uint8_t*>(q.data_ptr()), scale.data_ptr<float>(), amax.data_ptr<float>(),
+                         x.numel(), cur());
+}
+
 void fused_update(Tensor dW32, const Tensor& table, Tensor flat, Tensor grad, Tensor m, Tensor v, Tensor shadow, Tensor Wf,
                   Tensor Wd, const Tensor& step, const c10::optional<Tensor>& lr_scale, double lr, double decay,
                   double beta1, double beta2, double eps, int64_t dense_off, int64_t n_trainable) {
@@ -300,6 +310,7 @@ TORCH_LIBRARY_FRAGMENT(hefl, m) {
   m.def("set_head_cluster(int on) -> ()", [](int64_t on) { g_head_cluster = (int)on; });
   m.def("set_pdl(int on) -> ()", [](int64_t on) { hefl::nn::set_pdl((int)on); });
   m.def("wgrad0_gather(Tensor X, Tensor g, Tensor amax, Tensor(a!) dW32, int B, int H, int W) -> ()", &wgrad0_gather);
+  m.def("fp8_quantize(Tensor x, Tensor(a!) q, Tensor scale, Tensor(b!) amax) -> ()", &fp8_quantize);
   m.def("bn_forward(Tensor x, Tensor? res, Tensor gamma, Tensor beta, Tensor(a!)? run_mean, Tensor(b!)? run_var, Tensor(c!) mean, Tensor(d!) invstd, Tensor(e!) sums, Tensor(f!) y, float momentum, float eps, bool relu) -> ()", &bn_forward);
   m.def("bn_backward(Tensor dy, Tensor x, Tensor y, Tensor mean, Tensor invstd, Tensor gamma, Tensor(a!) sums, Tensor(b!) dx, Tensor(c!)? dres, bool relu) -> ()", &bn_backward);
   m.def("avgpool_forward(Tensor x, Tensor(a!) out, int B, int HW, int C) -> ()", &avgpool_forward);

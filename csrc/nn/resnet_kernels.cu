@@ -266,3 +266,45 @@ void avgpool_backward(const float* dout, void* dx, int B, int HW, int C, cudaStr
 
 }  // namespace nn
 }  // namespace hefl
+
+// ------------------------------------------------------------------------------------------
+// FP8 (e4m3) quantisation with delayed scaling for the 1x1 convolutions of ResNet-50 (BASELINE configs[4]:
+// "ResNet-50 fp8 local training"). One pass: q = sat_e4m3(x * scale) with the scale derived from the PREVIOUS
+// step's amax, and this step's amax recorded for the next one. The GEMM itself is a plain library GEMM
+// (cuBLASLt fp8 through torch._scaled_mm); this kernel replaces the amax + scale + cast passes around it.
+// ------------------------------------------------------------------------------------------
+#include <cuda_fp8.h>
+
+namespace hefl {
+namespace nn {
+
+__global__ void fp8_quantize_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ q,
+                                    const float* __restrict__ scale, float* __restrict__ amax, int64_t n8) {
+  const float s = *scale;
+  float local = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(x)[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t out[2] = {0u, 0u};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a = __uint_as_float(w[k] << 16), b = __uint_as_float(w[k] & 0xFFFF0000u);
+      local = fmaxf(local, fmaxf(fabsf(a), fabsf(b)));
+      const __nv_fp8x2_storage_t p = __nv_cvt_float2_to_fp8x2(make_float2(a * s, b * s), __NV_SATFINITE, __NV_E4M3);
+      out[k >> 1] |= (uint32_t)p << ((k & 1) * 16);
+    }
+    reinterpret_cast<uint2*>(q)[i] = make_uint2(out[0], out[1]);
+  }
+  for (int off = 16; off; off >>= 1) local = fmaxf(local, __shfl_xor_sync(0xffffffffu, local, off));
+  if ((threadIdx.x & 31) == 0 && local > 0.f) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(local));   // non-negative floats order as ints
+}
+
+void fp8_quantize(const void* x, uint8_t* q, const float* scale, float* amax, int64_t n, cudaStream_t st) {
+  const int64_t n8 = n / 8;
+  fp8_quantize_kernel<<<blocks_for(n8, 256 * 4, 148 * 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), q, scale,
+                                                                       amax, n8);
+  hefl::cuda::note_launch();
+}
+
+}  // namespace nn
+}  // namespace hefl

@@ -55,7 +55,13 @@ class LocalTrainer:
         self.v = torch.zeros(n, dtype=torch.float32, device=device)
         self.step_t = torch.zeros(1, dtype=torch.int64, device=device)
         self.lr_scale = torch.ones(1, dtype=torch.float32, device=device)
-        self.amp_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[cfg.dtype]
+        # "fp8": bf16 autocast + e4m3 GEMMs for the 1x1 convolutions of the ResNets (ops/fp8.py)
+        self.amp_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32,
+                          "fp8": torch.bfloat16}[cfg.dtype]
+        if cfg.dtype == "fp8":
+            from ..ops import fp8 as _fp8
+
+            _fp8.ENABLE = self.cuda
         B, S, C = cfg.batch_size, cfg.image_size, cfg.in_channels
         self.static_x = torch.zeros(B, S, S, C, dtype=torch.uint8, device=device)
         self.static_y = torch.zeros(B, dtype=torch.int64, device=device)

@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..ops.fp8 import Conv1x1
 from ..ops.resnet_ops import bn_act, global_avgpool
 
 
@@ -24,7 +25,7 @@ class BasicBlock(nn.Module):
         self.bn2 = nn.BatchNorm2d(planes)
         self.down = None
         if stride != 1 or cin != planes:
-            self.down = nn.Sequential(nn.Conv2d(cin, planes, 1, stride, bias=False), nn.BatchNorm2d(planes))
+            self.down = nn.Sequential(Conv1x1(cin, planes, stride), nn.BatchNorm2d(planes))
 
     def forward(self, x):
         idt = x if self.down is None else bn_act(self.down[1], self.down[0](x), relu=False)
@@ -37,15 +38,15 @@ class Bottleneck(nn.Module):
 
     def __init__(self, cin: int, planes: int, stride: int = 1):
         super().__init__()
-        self.conv1 = nn.Conv2d(cin, planes, 1, bias=False)
+        self.conv1 = Conv1x1(cin, planes)
         self.bn1 = nn.BatchNorm2d(planes)
         self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
         self.bn2 = nn.BatchNorm2d(planes)
-        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.conv3 = Conv1x1(planes, planes * 4)
         self.bn3 = nn.BatchNorm2d(planes * 4)
         self.down = None
         if stride != 1 or cin != planes * 4:
-            self.down = nn.Sequential(nn.Conv2d(cin, planes * 4, 1, stride, bias=False), nn.BatchNorm2d(planes * 4))
+            self.down = nn.Sequential(Conv1x1(cin, planes * 4, stride), nn.BatchNorm2d(planes * 4))
 
     def forward(self, x):
         idt = x if self.down is None else bn_act(self.down[1], self.down[0](x), relu=False)

@@ -110,7 +110,11 @@ class FederatedRunner:
         out = torch.empty_like(flat)
         k = float(self.transport.contributors())
         seed = (self.cfg.seed * 1_000_003 + self.round * 1009 + self.rank) & 0x7FFFFFFFFFFFFFFF
-        s_enc, s_comm, s_dec = (torch.cuda.Stream(dev) for _ in range(3))
+        # the three streams live as long as the runner: the caching allocator keeps one pool per stream, so
+        # fresh streams every round meant fresh cudaMallocs (and cudaFree stalls) every round
+        if getattr(self, "_pipe_streams", None) is None:
+            self._pipe_streams = tuple(torch.cuda.Stream(dev) for _ in range(3))
+        s_enc, s_comm, s_dec = self._pipe_streams
         cur = torch.cuda.current_stream(dev)
         for st in (s_enc, s_comm, s_dec):
             st.wait_stream(cur)

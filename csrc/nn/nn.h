@@ -17,7 +17,8 @@ void adam_step(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_
 void conv_fwd_pool(const void* X, const void* Wf, const float* bias, void* out, uint8_t* argmax, int B, int H,
                    int W, int CK, int CO, int spack, cudaStream_t st);
 void conv_set_debug(int mask);
-void conv_dgrad(const void* dY, const void* Wd, void* dX, int B, int H, int W, int CK, int CO, cudaStream_t st);
+void conv_dgrad(const void* dY, const void* Wd, void* dX, int B, int H, int W, int CK, int CO, const uint8_t* up_amax,
+                int up_W, cudaStream_t st);
 void conv_wgrad(const void* X, const void* DY, float* dW32, int B, int H, int W, int CK, int Co, cudaStream_t st);
 
 // Dense head (Flatten -> Dense/ReLU -> Dense/ReLU -> Dense -> softmax-CE) forward + backward.

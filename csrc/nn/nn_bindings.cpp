@@ -95,11 +95,22 @@ void conv_fwd_pool(const Tensor& X, const Tensor& Wf, const Tensor& bias, Tensor
                           (int)W, (int)CK, (int)CO, spack ? 1 : 0, cur());
 }
 
+// up_amax given: the un-pooling of the previous layer is fused into the epilogue — dX is then that layer's
+// conv-grid gradient [B*up_W*up_W, CO] (H = W = (up_W - 2) / 2 of this call), written at the arg-max positions.
 void conv_dgrad(const Tensor& dY, const Tensor& Wd, Tensor dX, int64_t B, int64_t H, int64_t W, int64_t CK,
-                int64_t CO) {
+                int64_t CO, const c10::optional<Tensor>& up_amax, int64_t up_W) {
   chk_bf16(dY, "dY"); chk_bf16(Wd, "Wd"); chk_bf16(dX, "dX");
-  TORCH_CHECK(dY.numel() == B * H * W * CK && dX.numel() == B * H * W * CO && Wd.numel() == 9 * CO * CK, "shape mismatch");
-  hefl::nn::conv_dgrad(dY.data_ptr(), Wd.data_ptr(), dX.data_ptr(), (int)B, (int)H, (int)W, (int)CK, (int)CO, cur());
+  TORCH_CHECK(dY.numel() == B * H * W * CK && Wd.numel() == 9 * CO * CK, "shape mismatch");
+  const uint8_t* up = nullptr;
+  if (up_amax.has_value()) {
+    TORCH_CHECK(up_amax->is_cuda() && up_amax->scalar_type() == at::kByte && up_amax->numel() == B * H * W * CO, "bad up_amax");
+    TORCH_CHECK(H == W && (up_W - 2) / 2 == H && dX.numel() == B * up_W * up_W * CO, "fused un-pool: dX must be [B*up_W*up_W, CO]");
+    up = up_amax->data_ptr<uint8_t>();
+  } else {
+    TORCH_CHECK(dX.numel() == B * H * W * CO, "dX must be [B*H*W, CO]");
+  }
+  hefl::nn::conv_dgrad(dY.data_ptr(), Wd.data_ptr(), dX.data_ptr(), (int)B, (int)H, (int)W, (int)CK, (int)CO, up, (int)up_W,
+                       cur());
 }
 
 void conv_wgrad(const Tensor& X, const Tensor& DY, Tensor dW32, int64_t B, int64_t H, int64_t W, int64_t CK, int64_t Co) {
@@ -300,7 +311,7 @@ TORCH_LIBRARY_FRAGMENT(hefl, m) {
   m.def("adam_step_(Tensor(a!) p, Tensor(b!) g, Tensor(c!) m, Tensor(d!) v, Tensor? shadow, Tensor step, Tensor? lr_scale, float lr, float decay, float beta1, float beta2, float eps) -> ()", &adam_step_);
   m.def("gather_h2d_(Tensor(a!) dst, Tensor src, Tensor indices) -> ()", &gather_h2d_);
   m.def("conv_fwd_pool(Tensor X, Tensor Wf, Tensor bias, Tensor(a!) out, Tensor(b!)? argmax, int B, int H, int W, int CK, int CO, bool spack=False) -> ()", &conv_fwd_pool);
-  m.def("conv_dgrad(Tensor dY, Tensor Wd, Tensor(a!) dX, int B, int H, int W, int CK, int CO) -> ()", &conv_dgrad);
+  m.def("conv_dgrad(Tensor dY, Tensor Wd, Tensor(a!) dX, int B, int H, int W, int CK, int CO, Tensor? up_amax=None, int up_W=0) -> ()", &conv_dgrad);
   m.def("conv_wgrad(Tensor X, Tensor DY, Tensor(a!) dW32, int B, int H, int W, int CK, int Co) -> ()", &conv_wgrad);
   m.def("preprocess_u8(Tensor x, Tensor? theta, Tensor(a!) X, int aug_seed, Tensor? step, bool spack=False) -> ()", &preprocess_u8);
   m.def("unpool_relu(Tensor g, Tensor amax, Tensor ypool, Tensor(a!) dY, int B, int H, int W, int Co) -> ()", &unpool_relu);

@@ -68,6 +68,9 @@ class MedCNNEngine:
         # layer-1 input carries pixels (w, w+1, w+2) in its 16 channels: 3 tap-GEMMs instead of 9 (conv_tcgen05.cu TS=1)
         self.spack0 = (os.environ.get("HEFL_SPACK0", "1") != "0" and self.Ci[0] == 3 and self.CK[0] == 16
                        and self.Co[0] == 32)
+        # un-pool inside the dgrad epilogue: correct (bit-exact test) but measured 10 us/step SLOWER than the
+        # separate un-pool kernels (the epilogue is issue-bound; 4x the stores), so off by default
+        self.fuse_unpool = os.environ.get("HEFL_FUSE_UNPOOL", "0") == "1"
         # layer-1 weight gradient by gather from the pooled gradient (csrc/nn/wgrad_gather.cu)
         self.gather_wgrad0 = (os.environ.get("HEFL_GATHER_WGRAD0", "1") != "0" and self.Co[0] == 32
                               and self.CK[0] == 16 and self.H[0] <= 256)
@@ -229,6 +232,7 @@ class MedCNNEngine:
             g = feat.grad.to(torch.bfloat16).view_as(feat_bf).contiguous()
         main = torch.cuda.current_stream(self.device)
         split = False
+        dy_ready = False
         for l in range(self.n - 1, -1, -1):
             h = self.H[l]
             if l == 0 and self.gather_wgrad0:
@@ -248,7 +252,9 @@ class MedCNNEngine:
             xin = self.X0[slot] if l == 0 else self.X[l]
             if self.dY[l] is None:
                 self.dY[l] = torch.zeros(self.P[l], self.Co[l], dtype=torch.bfloat16, device=self.device)
-            self.ops.unpool_relu(g, self.amax[l], self.X[l + 1], self.dY[l], self.B, h, h, self.Co[l])
+            if not dy_ready:
+                self.ops.unpool_relu(g, self.amax[l], self.X[l + 1], self.dY[l], self.B, h, h, self.Co[l])
+            dy_ready = False
             if self.two_streams and l > 0:
                 # wgrad(l) only needs X[l] and dY[l]; dgrad(l) -> unpool(l-1) -> ... proceeds meanwhile
                 self.side.wait_stream(main)
@@ -257,8 +263,17 @@ class MedCNNEngine:
             else:
                 self.ops.conv_wgrad(xin, self.dY[l], self._dw(l), self.B, h, h, self.CK[l], self.Co[l])
             if l > 0:
-                self.ops.conv_dgrad(self.dY[l], self._wd(l), self.gX[l], self.B, h, h, self.Co[l], self.Ci[l])
-                g = self.gX[l]
+                # dgrad(l) scatters its result straight into the conv-grid gradient of layer l-1 (un-pool fused
+                # into the epilogue) unless that layer takes the gather path, which wants the pooled gradient
+                if self.fuse_unpool and not (l == 1 and self.gather_wgrad0):
+                    if self.dY[l - 1] is None:
+                        self.dY[l - 1] = torch.zeros(self.P[l - 1], self.Co[l - 1], dtype=torch.bfloat16, device=self.device)
+                    self.ops.conv_dgrad(self.dY[l], self._wd(l), self.dY[l - 1], self.B, h, h, self.Co[l], self.Ci[l],
+                                        self.amax[l - 1], self.H[l - 1])
+                    dy_ready = True
+                else:
+                    self.ops.conv_dgrad(self.dY[l], self._wd(l), self.gX[l], self.B, h, h, self.Co[l], self.Ci[l])
+                    g = self.gX[l]
         if self.two_streams:
             main.wait_stream(self.side)
         if self.fused_step:

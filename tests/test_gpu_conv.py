@@ -116,6 +116,25 @@ def test_unpool_relu_matches_autograd():
     assert torch.equal(dY.view(B, H, H, Co).float(), ref)
 
 
+def test_dgrad_with_fused_unpool_equals_dgrad_then_unpool():
+    """conv_dgrad(up_amax=...) == conv_dgrad followed by unpool_relu of the previous layer, bit for bit."""
+    B, Hc, Cprev, Cout = 2, 30, 32, 64          # previous layer: conv grid 30x30 -> pooled 14x14 = this layer's input
+    H = (Hc - 2) // 2
+    g = torch.Generator(device="cuda").manual_seed(13)
+    dY = _bf(torch.randn(B * H * H, Cout, device="cuda", generator=g))
+    Wd = _bf(torch.randn(9, Cprev, Cout, device="cuda", generator=g) * 0.1)
+    code = torch.randint(0, 8, (B * H * H, Cprev), dtype=torch.uint8, device="cuda", generator=g)
+    ypool = ((code & 4) != 0).to(torch.bfloat16)            # the separate kernel masks by pooled > 0
+    gX = torch.zeros(B * H * H, Cprev, dtype=torch.bfloat16, device="cuda")
+    ops.conv_dgrad(dY, Wd.view(-1), gX, B, H, H, Cout, Cprev)
+    ref = torch.full((B * Hc * Hc, Cprev), 7.0, dtype=torch.bfloat16, device="cuda")
+    ops.unpool_relu(gX, code, ypool, ref, B, Hc, Hc, Cprev)
+    got = torch.zeros(B * Hc * Hc, Cprev, dtype=torch.bfloat16, device="cuda")
+    ops.conv_dgrad(dY, Wd.view(-1), got, B, H, H, Cout, Cprev, code, Hc)
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref)
+
+
 def test_preprocess_matches_grid_sample():
     B, H = 4, 64
     g = torch.Generator(device="cuda").manual_seed(6)
@@ -252,8 +271,8 @@ def test_wgrad0_gather_matches_autograd(H):
     assert (dW32[144] - ref_b).abs().max() <= 2e-3 * ref_b.abs().max() + 1e-3
 
 
-@pytest.mark.parametrize("gather", [True, False])
-def test_engine_gradients_match_autograd(gather):
+@pytest.mark.parametrize("gather,fuse", [(True, True), (False, True), (True, False)])
+def test_engine_gradients_match_autograd(gather, fuse):
     """Whole medical CNN: engine forward/backward vs PyTorch autograd on the same weights."""
     from hefl_b200.config import FLConfig
     from hefl_b200.models import ParamPack, create_model
@@ -269,6 +288,7 @@ def test_engine_gradients_match_autograd(gather):
     eng = MedCNNEngine(model, pack, cfg, dev)
     eng.fused_step = False          # keep the gradients in pack.grad (the fused update consumes them in place)
     eng.gather_wgrad0 = gather      # layer-1 weight gradient: gather kernel vs unpool + tensor-core wgrad
+    eng.fuse_unpool = fuse          # un-pool inside the dgrad epilogue vs separate kernels
     g = torch.Generator(device="cuda").manual_seed(7)
     x = torch.randint(0, 256, (8, 256, 256, 3), dtype=torch.uint8, device="cuda", generator=g)
     y = torch.randint(0, 2, (8,), device="cuda", generator=g)

@@ -70,7 +70,8 @@ class MedCNNEngine:
                        and self.Co[0] == 32)
         # un-pool inside the dgrad epilogue: correct (bit-exact test) but measured 10 us/step SLOWER than the
         # separate un-pool kernels (the epilogue is issue-bound; 4x the stores), so off by default
-        self.fuse_unpool = os.environ.get("HEFL_FUSE_UNPOOL", "0") == "1"
+        self.fuse_unpool = os.environ.get("HEFL_FUSE_UNPOOL", "0") != "0"
+        self.fuse_from = int(os.environ.get("HEFL_FUSE_UNPOOL_FROM", "0"))     # fuse only into layers >= this index
         # layer-1 weight gradient by gather from the pooled gradient (csrc/nn/wgrad_gather.cu)
         self.gather_wgrad0 = (os.environ.get("HEFL_GATHER_WGRAD0", "1") != "0" and self.Co[0] == 32
                               and self.CK[0] == 16 and self.H[0] <= 256)
@@ -265,7 +266,7 @@ class MedCNNEngine:
             if l > 0:
                 # dgrad(l) scatters its result straight into the conv-grid gradient of layer l-1 (un-pool fused
                 # into the epilogue) unless that layer takes the gather path, which wants the pooled gradient
-                if self.fuse_unpool and not (l == 1 and self.gather_wgrad0):
+                if self.fuse_unpool and l - 1 >= self.fuse_from and not (l == 1 and self.gather_wgrad0):
                     if self.dY[l - 1] is None:
                         self.dY[l - 1] = torch.zeros(self.P[l - 1], self.Co[l - 1], dtype=torch.bfloat16, device=self.device)
                     self.ops.conv_dgrad(self.dY[l], self._wd(l), self.dY[l - 1], self.B, h, h, self.Co[l], self.Ci[l],

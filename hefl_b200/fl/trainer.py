@@ -8,11 +8,15 @@ factor 0.3, floor 1e-6, :187), ModelCheckpoint on best training accuracy (:189-1
 augmentation shear/zoom/flip and 1/255 rescale (:80-86).
 
 B200 design: parameters, gradients and Adam moments are flat fp32 buffers (``ParamPack``),
-the optimiser is one fused kernel, the whole step (preprocess -> forward -> backward -> Adam)
-is captured in a CUDA graph and replayed, the learning-rate scale and step counter live on
-the device, and losses are read back asynchronously (one sync per epoch, not per step).
-Two NN backends: ``cudnn`` (PyTorch autograd + cuDNN/cuBLAS in bf16 autocast — the baseline)
-and ``tcgen05`` (hand-written implicit-GEMM kernels, ``hefl_b200.ops.conv``).
+the optimiser is one fused kernel, the step (forward -> backward -> Adam) is captured in a CUDA
+graph and replayed, the learning-rate scale and step counter live on the device, and losses are
+read back asynchronously (one sync per epoch, not per step). With the tcgen05 engine an epoch is
+a four-stream software pipeline: H2D / gather + pre-processing of batch i+1 (prep stream), the
+graph of step i (main + the engine's side stream), the loss read-back of step i-1 (stats stream);
+the first batch of the next pass (validation, next epoch) is staged under the last step.
+Two NN backends: ``cudnn`` (PyTorch autograd + cuDNN/cuBLAS in bf16 autocast, fused BN kernels and
+optional fp8 1x1 convolutions for the ResNets — also the baseline arm) and ``tcgen05``
+(hand-written kernels, ``hefl_b200.ops.conv_engine``).
 """
 from __future__ import annotations
 

@@ -1,17 +1,23 @@
-"""Training engine for the sequential 3x3-conv CNNs on the hand-written tcgen05 kernels.
+"""Training engine for the sequential 3x3-conv CNNs on the hand-written sm_100a kernels.
 
 Replaces Keras' ``model.fit`` compute path (FLPyfhelin.py:118-136, :193) for the medical CNN:
 
-  forward   preprocess_u8 (uint8 -> bf16 NHWC, 1/255, affine augmentation)
-            6 x conv_fwd_pool  (TMA-fed tcgen05 implicit GEMM, bias+ReLU+2x2 max-pool+argmax
-                                fused in the TMEM epilogue; only pooled tensors reach HBM)
-            dense head + softmax cross-entropy (tiny: PyTorch/cuBLAS autograd, fp32)
-  backward  6 x unpool_relu (pooled grad -> conv-grid grad in [P,C] and [C,P] layouts)
-            6 x conv_wgrad  (tcgen05, taps stacked along M, split-K, bias grad as a ones row)
-            5 x conv_dgrad  (tcgen05 tap GEMM with negative offsets)
-            conv_grad_finalize -> flat fp32 gradient, then the fused Adam kernel (trainer)
+  input     preprocess_u8 (uint8 -> bf16 NHWC [P,16], 1/255, Philox affine augmentation; layer-1 input
+            carries pixels w, w+1, w+2 in its channels) into one of two X0 slots — the trainer stages
+            batch i+1 on a side stream while step i runs
+  forward   6 x conv_fwd_pool  (TMA-fed tcgen05 tap GEMMs, bias + ReLU + 2x2 max-pool + 3-bit
+                                arg-max/active code fused in the TMEM epilogue; only pooled tensors
+                                reach HBM)
+            head_forward_backward (Dense 128-64-C + softmax CE, forward AND backward, one launch on a
+                                   cluster of 8 CTAs)
+  backward  unpool_relu / conv_dgrad chain on the main stream (layers 6..2),
+            conv_wgrad (tcgen05, MN-major operands, split-K RED) on a side stream,
+            layer 1: wgrad0_gather straight from the pooled gradient (no un-pool, no dY tensor)
+  update    conv_grad_finalize + Adam + conv_weight_relayout: layers 2..6 and the head on the side
+            stream under the layer-1 kernel, the 896 layer-1 parameters in the tail (``opt`` hooks)
 
-All buffers are allocated once; the whole step is CUDA-graph capturable.
+All buffers are allocated once; a step is CUDA-graph capturable (one graph per input slot); every
+kernel uses programmatic dependent launch (csrc/nn/launch.cuh).
 """
 from __future__ import annotations
 

@@ -129,22 +129,54 @@ __global__ void __launch_bounds__(hc::NT, 1) head_cluster_kernel(const HeadClust
   // every CTA of the cluster has started (its shared memory is live) before anyone writes into it
   cluster.sync();
 
-  // ---- P1: h1[:, own 16]
+  // ---- P1: h1[:, own 16]. Register-tiled: every lane owns a 4-sample x 4-neuron tile and every warp one
+  // eighth of K (8 LDS.128 per 64 FMAs; the first version did 3 LDS.128 per 8 FMAs and spent 30 % of the
+  // kernel here, shared-memory bound). Partial sums of the 8 warps meet in shared memory (the dh1 buffer is
+  // idle until P4).
   {
+    const int lane = t & 31, warp = t >> 5;
+    const int bi = lane >> 2, ji = lane & 3;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const float* fbase = featS + (4 * bi) * FP + warp * (F / 8);
+    const float* wbase = w1r + (4 * ji) * FP + warp * (F / 8);
+#pragma unroll 2
+    for (int k = 0; k < F / 8; k += 4) {
+      float4 f[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        f[i] = *reinterpret_cast<const float4*>(fbase + i * FP + k);
+        w[i] = *reinterpret_cast<const float4*>(wbase + i * FP + k);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[i][j] = fmaf(f[i].x, w[j].x, acc[i][j]);
+          acc[i][j] = fmaf(f[i].y, w[j].y, acc[i][j]);
+          acc[i][j] = fmaf(f[i].z, w[j].z, acc[i][j]);
+          acc[i][j] = fmaf(f[i].w, w[j].w, acc[i][j]);
+        }
+    }
+    float* part = dh1S + warp * (BM * J1);                    // [8 warps][32 samples][16 neurons]
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(part + (4 * bi + i) * J1 + 4 * ji) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    __syncthreads();
     const int b = t >> 3, jq = t & 7;
     if (b < B) {
-      const float4* f4 = reinterpret_cast<const float4*>(featS + b * FP);
-      const float4* wa = reinterpret_cast<const float4*>(w1r + jq * FP);
-      const float4* wb = reinterpret_cast<const float4*>(w1r + (jq + 8) * FP);
-      float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
-#pragma unroll 4
-      for (int k = 0; k < F / 4; ++k) {
-        const float4 f = f4[k], x = wa[k], y = wb[k];
-        a0 = fmaf(f.x, x.x, a0); a1 = fmaf(f.y, x.y, a1); a0 = fmaf(f.z, x.z, a0); a1 = fmaf(f.w, x.w, a1);
-        c0 = fmaf(f.x, y.x, c0); c1 = fmaf(f.y, y.y, c1); c0 = fmaf(f.z, y.z, c0); c1 = fmaf(f.w, y.w, c1);
+      float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        v0 += dh1S[w * (BM * J1) + b * J1 + jq];
+        v1 += dh1S[w * (BM * J1) + b * J1 + jq + 8];
       }
       const int j0 = r * J1 + jq, j1 = j0 + 8;
-      float v0 = a0 + a1 + __ldg(a.b1 + j0), v1 = c0 + c1 + __ldg(a.b1 + j1);
+      v0 += __ldg(a.b1 + j0);
+      v1 += __ldg(a.b1 + j1);
       v0 = v0 > 0.f ? v0 : 0.f;
       v1 = v1 > 0.f ? v1 : 0.f;
 #pragma unroll

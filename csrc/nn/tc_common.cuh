@@ -30,7 +30,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
-// Spin on the phase parity; traps (instead of hanging the GPU) after ~2 s.
+// Wait on the phase parity; traps (instead of hanging the GPU) after ~2 s. The suspend-time hint lets the
+// hardware park the warp until the phase completes instead of returning to a software spin loop: with ~30
+// waiting warps per SM the spin instructions were competing with the epilogue for issue slots.
+#ifndef HEFL_MBAR_SUSPEND_NS
+#define HEFL_MBAR_SUSPEND_NS 1000000
+#endif
+constexpr uint32_t kMbarSuspendNs = HEFL_MBAR_SUSPEND_NS;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
@@ -39,10 +45,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(kMbarSuspendNs)
         : "memory");
     if (done) break;
     if ((++spins & 0xFFFu) == 0) {

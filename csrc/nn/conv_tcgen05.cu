@@ -122,7 +122,16 @@ struct TapGemmArgs {
   // 2x2 window on the previous layer's conv grid (up_W x up_W per image), zeros to the other three positions.
   const uint8_t* up_amax;   // [P, co_total] codes of the previous layer (bits 0-1 position, bit 2 active) or null
   int up_W;
+  // tile -> (image, row pair, column tile) without integer division: q = umulhi(n, magic) is exact for
+  // n, d < 2^16 with magic = ceil(2^32 / d) (the epilogue warps spent ~40 of their ~100 per-tile set-up
+  // instructions in two software divisions)
+  uint32_t magic_per_img, magic_tiles_w;
 };
+
+__device__ __forceinline__ int fast_div(int n, int d, uint32_t magic) {
+  if (d == 1) return n;
+  return magic ? (int)__umulhi((uint32_t)n, magic) : n / d;
+}
 
 // TS = filter taps along the image row that are separate GEMMs: 3 normally; 1 when the three horizontal taps
 // are packed into the channel dimension by the producer of the input (layer 1: 3 channels x 3 taps = 9 of the
@@ -220,9 +229,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int base, seg_stride;
         if (POOL) {
           const int per_img = a.Hp * a.tiles_w;
-          const int b = t / per_img;
+          const int b = fast_div(t, per_img, a.magic_per_img);
           const int rem = t - b * per_img;
-          const int hp = rem / a.tiles_w;
+          const int hp = fast_div(rem, a.tiles_w, a.magic_tiles_w);
           const int tw = rem - hp * a.tiles_w;
           base = (b * a.H + 2 * hp) * a.W + tw * 128;
           seg_stride = a.W;                      // segment j = image row h + j
@@ -305,9 +314,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_after();
       if (POOL) {
         const int per_img = a.Hp * a.tiles_w;
-        const int b = t / per_img;
+        const int b = fast_div(t, per_img, a.magic_per_img);
         const int rem = t - b * per_img;
-        const int hp = rem / a.tiles_w;
+        const int hp = fast_div(rem, a.tiles_w, a.magic_tiles_w);
         const int tw = rem - hp * a.tiles_w;
         const int col = tw * 128 + qd * 32 + lane;           // conv-output column of this thread
         const int wp = col >> 1;
@@ -438,6 +447,12 @@ void conv_fwd_pool(const void* X, const void* Wf, const float* bias, void* out, 
   a.Hp = (H - 2) / 2; a.Wp = (W - 2) / 2;
   a.tiles_w = (2 * a.Wp + 127) / 128;
   a.num_tiles = B * a.Hp * a.tiles_w;
+  {
+    const int per_img = a.Hp * a.tiles_w;
+    const bool ok = a.num_tiles < 65536 && per_img > 1 && per_img < 65536;
+    a.magic_per_img = ok ? (uint32_t)((0x100000000ull + per_img - 1) / per_img) : 0u;
+    a.magic_tiles_w = (ok && a.tiles_w > 1) ? (uint32_t)((0x100000000ull + a.tiles_w - 1) / a.tiles_w) : 0u;
+  }
   a.P = B * H * W;
   a.co_total = CO;
   a.bias = bias;

@@ -72,11 +72,14 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_
     }
   }
   __syncthreads();
+  // thread = (row lane, 8-channel group): no division inside the loop (a 64-bit t / groups per element cost
+  // more than the loads)
   const int groups = C >> 3;
-  const int64_t total = P * groups;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(t % groups);
-    const int64_t o = (t / groups) * C + cg * 8;
+  const int cg = threadIdx.x % groups;
+  const int rows_per_iter = blockDim.x / groups;
+  for (int64_t row = (int64_t)blockIdx.x * rows_per_iter + threadIdx.x / groups; row < P;
+       row += (int64_t)gridDim.x * rows_per_iter) {
+    const int64_t o = row * C + cg * 8;
     const uint4 v = *reinterpret_cast<const uint4*>(x + o);
     uint4 rv = make_uint4(0u, 0u, 0u, 0u);
     if (res) rv = *reinterpret_cast<const uint4*>(res + o);
@@ -166,11 +169,14 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const 
     ss[2 * C + c] = -a * sums[c] * invP - b * mean[c];
   }
   __syncthreads();
+  // thread = (row lane, 8-channel group): no division inside the loop (a 64-bit t / groups per element cost
+  // more than the loads)
   const int groups = C >> 3;
-  const int64_t total = P * groups;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(t % groups);
-    const int64_t o = (t / groups) * C + cg * 8;
+  const int cg = threadIdx.x % groups;
+  const int rows_per_iter = blockDim.x / groups;
+  for (int64_t row = (int64_t)blockIdx.x * rows_per_iter + threadIdx.x / groups; row < P;
+       row += (int64_t)gridDim.x * rows_per_iter) {
+    const int64_t o = row * C + cg * 8;
     const uint4 dv = *reinterpret_cast<const uint4*>(dy + o);
     const uint4 xv = *reinterpret_cast<const uint4*>(x + o);
     uint4 yv = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
@@ -215,7 +221,7 @@ void bn_forward(const void* x, const void* res, const float* gamma, const float*
   const int rows_per_iter = threads / (C / 8);
   bn_stats_kernel<<<blocks_for(P, rows_per_iter * 8, 148 * 4), threads, 2 * C * 4, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), sums, P, C);
-  bn_apply_kernel<<<blocks_for(P * (C / 8), 256 * 4, 148 * 8), 256, 2 * C * 4, st>>>(
+  bn_apply_kernel<<<blocks_for(P, rows_per_iter * 4, 148 * 8), threads, 2 * C * 4, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(res), sums, gamma, beta, mean,
       invstd, run_mean, run_var, reinterpret_cast<__nv_bfloat16*>(y), P, C, momentum, eps, relu);
   hefl::cuda::note_launch(2);
@@ -229,7 +235,7 @@ void bn_backward(const void* dy, const void* x, const void* y, const float* mean
   bn_bwd_reduce_kernel<<<blocks_for(P, rows_per_iter * 8, 148 * 4), threads, 2 * C * 4, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x),
       reinterpret_cast<const __nv_bfloat16*>(y), mean, invstd, sums, P, C, relu);
-  bn_bwd_apply_kernel<<<blocks_for(P * (C / 8), 256 * 4, 148 * 8), 256, 3 * C * 4, st>>>(
+  bn_bwd_apply_kernel<<<blocks_for(P, rows_per_iter * 4, 148 * 8), threads, 3 * C * 4, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x),
       reinterpret_cast<const __nv_bfloat16*>(y), mean, invstd, gamma, sums, reinterpret_cast<__nv_bfloat16*>(dx),
       reinterpret_cast<__nv_bfloat16*>(dres), P, C, relu);

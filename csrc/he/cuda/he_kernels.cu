@@ -7,6 +7,9 @@
 
 #include "../kernels.h"
 #include "../philox.h"
+#include <stdexcept>
+#include <string>
+
 #include "ntt.cuh"
 
 namespace hefl {
@@ -14,7 +17,16 @@ namespace cuda {
 
 static std::atomic<uint64_t> g_launches{0};
 uint64_t launch_count() { return g_launches.load(); }
-void note_launch(uint64_t n) { g_launches.fetch_add(n); }
+// Called by every host launcher right after its launch(es): counts our kernels (bench.py gpu_launches) and
+// turns a failed launch (bad configuration, missing sm_100a image, sticky asynchronous error) into an exception
+// instead of a silent no-op — the ops must fail loudly.
+void note_launch(uint64_t n) {
+  g_launches.fetch_add(n);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    throw std::runtime_error(std::string("hefl: CUDA kernel launch failed: ") + cudaGetErrorName(e) + " (" +
+                             cudaGetErrorString(e) + ")");
+}
 
 using namespace hefl::dev;
 

@@ -489,6 +489,251 @@ void conv_dgrad(const void* dY, const void* Wd, void* dX, int B, int H, int W, i
 }
 
 // ------------------------------------------------------------------------------------------
+// G1b (opt-in, HEFL_FWD_PAIR): forward + pool with both columns of a pooling window in the SAME TMEM lane.
+// Validated against G1 on hardware (tests/test_gpu_conv.py::test_conv_fwd_pool_pair_matches_plain_kernel: same
+// pooled values and arg-max codes); 33.7 vs 40.4 us on layer 1 (B=32, 256x256), slower on the small layers.
+//
+// ncu on G1 (prof_fwd0_v4): the pool epilogue is the limiter of the forward kernels — 62 % issue-active,
+// 6 % tensor pipe, ~33 instructions per pooled output — because a lane owns one conv COLUMN, so the 2x2 window
+// needs a lane exchange (5 shuffles, 16 parity selects) per 8-channel chunk.
+//
+// Here the activation matrix [pixels, CK] is viewed as [pixel PAIRS, 2*CK] (same memory; needs an even image
+// width so pairs never straddle rows). GEMM row j of accumulator (dy, dx) is window j of the pooled row:
+//     acc(dy,dx)[j] = sum_{r,s} X[row 2hp+dy+r, column 2j+dx+s] . W[r,s]
+// With e = dx + s, column 2j+e is pair-row j + (e >> 1), half e & 1: a row shift of the A descriptor plus a
+// K byte offset of (e & 1) * CK * 2 inside the pair-row — both are things G1 already does (row-shifted starts,
+// 32-byte K steps inside a swizzle atom). Four accumulators (2 rows x 2 column parities), M = 128 windows.
+// The epilogue thread of window j then holds all four values of its window: max/arg-max in registers, no
+// shuffles, every lane stores a full 16-byte pooled pixel chunk. Restricted to CK <= 32 (one swizzle atom per
+// pair-row) and CO <= 64 (4 accumulators x 2 TMEM buffers).
+// ------------------------------------------------------------------------------------------
+template <int CK, int CO>
+struct PairFwdCfg {
+  static constexpr int ROW_BYTES = 2 * CK * 2;            // one pair-row: 2 pixels x CK channels, 64 or 128 B
+  static constexpr int NSEG = 4;                          // image rows 2hp .. 2hp+3
+  static constexpr int SEG_ROWS = 136;                    // 130 pair-rows used (128 windows + shift 1 + slack)
+  static constexpr int SEG_BYTES = SEG_ROWS * ROW_BYTES;
+  static constexpr int HALO = NSEG * SEG_BYTES;
+  static constexpr int W_ROW = CK * 2;                    // weight rows: [tap][CO][CK], 32 or 64 B (as G1)
+  static constexpr int W_TAP = CO * W_ROW;
+  static constexpr int W_BYTES = 9 * W_TAP;
+  static constexpr int BAR_BYTES = 384;
+  static constexpr int NBUF = 2;
+  static constexpr int SMEM = W_BYTES + NBUF * HALO + BAR_BYTES + 1024;
+  static constexpr int NACC = 4;
+  static constexpr int NT = 2;
+  static constexpr int ACC_COLS = NT * NACC * CO;
+  static constexpr int TMEM_COLS = ACC_COLS <= 256 ? 256 : 512;
+  static constexpr int OCC = (2 * SMEM <= 226 * 1024 && 2 * TMEM_COLS <= 512) ? 2 : 1;
+  static_assert(CK == 16 || CK == 32, "pair-row forward: one swizzle atom per pair-row");
+  static_assert(CO == 32 || CO == 64, "pair-row forward: 4 accumulators x 2 buffers must fit TMEM");
+  static_assert(SMEM <= 226 * 1024, "shared memory");
+};
+
+struct PairFwdArgs {
+  int B, H, W;          // input grid (W even)
+  int Hp, Wp;           // pooled grid
+  int num_tiles;        // B * Hp (one pooled row per tile; Wp <= 128)
+  const float* bias;
+  __nv_bfloat16* out;   // [B,Hp,Wp,CO]
+  uint8_t* argmax;      // may be null
+};
+
+template <int CK, int CO>
+__global__ void __launch_bounds__(352, PairFwdCfg<CK, CO>::OCC)
+pair_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                const PairFwdArgs a) {
+  using Cfg = PairFwdCfg<CK, CO>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + Cfg::W_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + Cfg::NBUF * Cfg::HALO);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::NBUF;
+  uint64_t* wfull = bars + 2 * Cfg::NBUF;
+  uint64_t* tfull = wfull + 1;
+  uint64_t* tempty = tfull + Cfg::NT;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + Cfg::NT);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 8 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmW);
+    for (int s = 0; s < Cfg::NBUF; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }   // two MMA issuers
+    mbar_init(wfull, 1);
+    for (int i = 0; i < Cfg::NT; ++i) { mbar_init(&tfull[i], 2); mbar_init(&tempty[i], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  if (warp == 8 && elect_one()) {
+    mbar_expect_tx(wfull, Cfg::W_BYTES);
+    for (int tap = 0; tap < 9; ++tap) tma_load_2d(sW + tap * Cfg::W_TAP, &tmW, 0, tap * CO, wfull);
+  }
+  pdl_wait();
+  const int half_w = a.W >> 1;
+
+  if (warp == 8) {
+    // ===== TMA producer: 4 image rows of pair-rows per tile =====
+    if (elect_one()) {
+      int buf = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+        const int b = t / a.Hp, hp = t - b * a.Hp;
+        const int q0 = (b * a.H + 2 * hp) * half_w;          // first pair-row of image row 2hp
+        mbar_wait(&empty[buf], phase ^ 1);
+        mbar_expect_tx(&full[buf], Cfg::HALO);
+        uint8_t* dst = sA + buf * Cfg::HALO;
+        for (int sg = 0; sg < Cfg::NSEG; ++sg) tma_load_2d(dst + sg * Cfg::SEG_BYTES, &tmA, 0, q0 + sg * half_w, &full[buf]);
+        if (++buf == Cfg::NBUF) { buf = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 9 || warp == 10) {
+    // ===== MMA issuers: warp 9 -> accumulators (dy=0, dx=0/1), warp 10 -> (dy=1, dx=0/1) =====
+    const int dy = warp - 9;
+    constexpr uint32_t idesc = make_idesc_bf16(128, CO);
+    mbar_wait(wfull, 0);
+    tc_fence_after();
+    int buf = 0, tb = 0;
+    uint32_t phase = 0, tb_phase = 0;
+    for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+      mbar_wait(&tempty[tb], tb_phase ^ 1);
+      mbar_wait(&full[buf], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_lo = desc_lo(smem_u32(sA + buf * Cfg::HALO));
+        const uint32_t w_lo = desc_lo(smem_u32(sW));
+        constexpr uint32_t a_hi = desc_hi(8 * Cfg::ROW_BYTES, Cfg::ROW_BYTES);
+        constexpr uint32_t w_hi = desc_hi(8 * Cfg::W_ROW, Cfg::W_ROW);
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const uint32_t d_tmem = tmem_base + (tb * Cfg::NACC + dy * 2 + dx) * CO;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int r = tap / 3, s = tap % 3;
+            const int e = dx + s;
+#pragma unroll
+            for (int k = 0; k < CK / 16; ++k) {
+              const uint32_t ao = ((dy + r) * Cfg::SEG_BYTES + (e >> 1) * Cfg::ROW_BYTES + (e & 1) * CK * 2 + k * 32) >> 4;
+              const uint32_t wo = (tap * Cfg::W_TAP + k * 32) >> 4;
+              umma_bf16_lh(d_tmem, a_lo + ao, a_hi, w_lo + wo, w_hi, idesc, (tap | k) != 0 ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(&empty[buf]);
+        umma_commit(&tfull[tb]);
+      }
+      __syncwarp();
+      if (++buf == Cfg::NBUF) { buf = 0; phase ^= 1; }
+      if (++tb == Cfg::NT) { tb = 0; tb_phase ^= 1; }
+    }
+  } else {
+    // ===== epilogue warps 0..7: lane = window (quadrant = warp % 4), channel chunks interleaved by warp / 4 =====
+    const int qd = warp & 3;
+    const int grp = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+    const int j = qd * 32 + lane;                          // window index in the pooled row
+    int tb = 0;
+    uint32_t tb_phase = 0;
+    for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+      mbar_wait(&tfull[tb], tb_phase);
+      tc_fence_after();
+      const size_t row_out = (size_t)t * a.Wp;             // t = b * Hp + hp
+#pragma unroll 1
+      for (int ch = grp; ch < CO / 8; ch += 2) {
+        float v00[8], v01[8], v10[8], v11[8];
+        const uint32_t tcol = tmem_base + lane_base + tb * Cfg::NACC * CO + ch * 8;
+        tmem_ld8_nowait(tcol + 0 * CO, v00);
+        tmem_ld8_nowait(tcol + 1 * CO, v01);
+        tmem_ld8_nowait(tcol + 2 * CO, v10);
+        tmem_ld8_nowait(tcol + 3 * CO, v11);
+        const float4 bA = __ldg(reinterpret_cast<const float4*>(a.bias + ch * 8));
+        const float4 bB = __ldg(reinterpret_cast<const float4*>(a.bias + ch * 8 + 4));
+        const float bias8[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+        tmem_ld_wait();
+        uint32_t packed[4], idx[2] = {0u, 0u};
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+          float x[2];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            // same tie-breaking as G1: lower row wins only if strictly greater, then right column likewise
+            const bool l0 = v10[c + i] > v00[c + i];
+            const bool l1 = v11[c + i] > v01[c + i];
+            const float m0 = l0 ? v10[c + i] : v00[c + i];
+            const float m1 = l1 ? v11[c + i] : v01[c + i];
+            const bool rw = m1 > m0;
+            const uint32_t rowbit = (rw ? l1 : l0) ? 1u : 0u;
+            const float y = (rw ? m1 : m0) + bias8[c + i];
+            idx[(c + i) >> 2] |= ((rowbit << 1) | (rw ? 1u : 0u) | (y > 0.f ? 4u : 0u)) << (((c + i) & 3) * 8);
+            x[i] = y > 0.f ? y : 0.f;
+          }
+          packed[c >> 1] = pack_bf16x2(x[0], x[1]);
+        }
+        if (j < a.Wp) {
+          const size_t o = (row_out + j) * CO + ch * 8;
+          *reinterpret_cast<uint4*>(a.out + o) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          if (a.argmax) *reinterpret_cast<uint2*>(a.argmax + o) = make_uint2(idx[0], idx[1]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[tb]);
+      if (++tb == Cfg::NT) { tb = 0; tb_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int CK, int CO>
+static void launch_pair_fwd(const __nv_bfloat16* X, const __nv_bfloat16* Wt, PairFwdArgs a, cudaStream_t st) {
+  using Cfg = PairFwdCfg<CK, CO>;
+  const uint64_t pair_rows = ((uint64_t)a.B * a.H * a.W) / 2;
+  const CUtensorMap tmA = make_map(X, 2 * CK, pair_rows, (uint64_t)Cfg::ROW_BYTES, 2 * CK, Cfg::SEG_ROWS);
+  const CUtensorMap tmW = make_map(Wt, CK, (uint64_t)9 * CO, (uint64_t)CK * 2, CK, CO);
+  auto kern = pair_fwd_kernel<CK, CO>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  int gx = num_sms() * Cfg::OCC;
+  if (gx > a.num_tiles) gx = a.num_tiles;
+  launch_pdl(kern, dim3(gx), dim3(352), Cfg::SMEM, st, tmA, tmW, a);
+  hefl::cuda::note_launch();
+}
+
+bool conv_fwd_pool_pair_supported(int H, int W, int CK, int CO) {
+  return H == W && (W % 2) == 0 && (W - 2) / 2 <= 128 && (CK == 16 || CK == 32) && (CO == 32 || CO == 64);
+}
+
+// Same contract as conv_fwd_pool (plain 9-tap weight layout [9][CO][CK]); see G1b above.
+void conv_fwd_pool_pair(const void* X, const void* Wf, const float* bias, void* out, uint8_t* argmax, int B, int H,
+                        int W, int CK, int CO, cudaStream_t st) {
+  if (!conv_fwd_pool_pair_supported(H, W, CK, CO)) throw std::runtime_error("conv_fwd_pool_pair: unsupported shape");
+  PairFwdArgs a{};
+  a.B = B; a.H = H; a.W = W;
+  a.Hp = (H - 2) / 2; a.Wp = (W - 2) / 2;
+  a.num_tiles = B * a.Hp;
+  a.bias = bias;
+  a.out = reinterpret_cast<__nv_bfloat16*>(out);
+  a.argmax = argmax;
+  const auto* x = reinterpret_cast<const __nv_bfloat16*>(X);
+  const auto* w = reinterpret_cast<const __nv_bfloat16*>(Wf);
+  if (CK == 16 && CO == 32) launch_pair_fwd<16, 32>(x, w, a, st);
+  else if (CK == 32 && CO == 32) launch_pair_fwd<32, 32>(x, w, a, st);
+  else if (CK == 32 && CO == 64) launch_pair_fwd<32, 64>(x, w, a, st);
+  else throw std::runtime_error("conv_fwd_pool_pair: unsupported (CK, CO)");
+}
+
+// ------------------------------------------------------------------------------------------
 // G2: weight-gradient kernel.
 //
 // dW[r,s][ci][co] = sum_m X[m + r*W + s][ci] * dY[m][co]. Both operands are consumed in their

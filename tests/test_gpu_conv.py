@@ -154,6 +154,26 @@ def test_preprocess_matches_grid_sample():
     assert (X.view(B, H, H, 16)[..., :3].float() - ref).abs().max() < 1e-2
 
 
+@pytest.mark.parametrize("B,H,Ci,CK,Co", [(2, 256, 3, 16, 32), (2, 62, 32, 32, 32), (3, 30, 32, 32, 64), (1, 20, 3, 16, 32)])
+def test_conv_fwd_pool_pair_matches_plain_kernel(B, H, Ci, CK, Co):
+    """Pair-row forward kernel (both window columns in one TMEM lane) == the tap-GEMM forward: pooled values and codes."""
+    g = torch.Generator(device="cuda").manual_seed(17)
+    P = B * H * H
+    X = torch.zeros(P + 8, CK, dtype=torch.bfloat16, device="cuda")
+    X[:P, :Ci] = _bf(torch.randn(P, Ci, device="cuda", generator=g))
+    Wf = torch.zeros(9, Co, CK, dtype=torch.bfloat16, device="cuda")
+    Wf[:, :, :Ci] = _bf(torch.randn(9, Co, Ci, device="cuda", generator=g) * 0.2)
+    bias = torch.randn(Co, device="cuda", generator=g) * 0.1
+    Hp = (H - 2) // 2
+    out0 = torch.zeros(B * Hp * Hp, Co, dtype=torch.bfloat16, device="cuda"); am0 = torch.zeros(B * Hp * Hp, Co, dtype=torch.uint8, device="cuda")
+    out1 = torch.zeros_like(out0); am1 = torch.zeros_like(am0)
+    ops.conv_fwd_pool(X[:P], Wf.view(-1), bias, out0, am0, B, H, H, CK, Co)
+    ops.conv_fwd_pool_pair(X, Wf.view(-1), bias, out1, am1, B, H, H, CK, Co)
+    torch.cuda.synchronize()
+    assert (out0.float() - out1.float()).abs().max() <= 2.0 ** -7 * out0.float().abs().max() + 1e-3
+    assert (am0 == am1).float().mean() > 0.999
+
+
 @pytest.mark.parametrize("H", [256, 70])
 def test_spack_first_layer_matches_torch(H):
     """s-packed first layer: preprocess_u8(spack) writes pixels (w, w+1, w+2) into the 16 channels and the

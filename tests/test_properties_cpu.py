@@ -84,3 +84,17 @@ def test_serialization_golden_bytes():
     assert len(raw) == hdr["offset"] + 2 * 3 * 4096 * 8
     back = ctx.ct_from_bytes(raw)
     assert torch.equal(back.data, ct.data) and back.nvals == 7 and back.scale == ctx.scale
+
+
+def test_reciprocal_division_used_by_the_conv_kernels_is_exact():
+    """csrc/nn/conv_tcgen05.cu::fast_div replaces n / d by umulhi(n, ceil(2^32 / d)) for tile indices
+    (n, d < 2^16, d > 1). The identity must hold for every value the host code allows."""
+    import random
+    rng = random.Random(0)
+    ds = list(range(2, 600)) + [rng.randrange(2, 65536) for _ in range(300)] + [65535]
+    for d in ds:
+        magic = ((1 << 32) + d - 1) // d
+        assert magic < (1 << 32)
+        ns = [0, 1, d - 1, d, d + 1, 2 * d - 1, 65535, 65534] + [rng.randrange(0, 65536) for _ in range(64)]
+        for n in ns:
+            assert (n * magic) >> 32 == n // d, (n, d)

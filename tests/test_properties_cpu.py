@@ -97,4 +97,5 @@ def test_reciprocal_division_used_by_the_conv_kernels_is_exact():
         assert magic < (1 << 32)
         ns = [0, 1, d - 1, d, d + 1, 2 * d - 1, 65535, 65534] + [rng.randrange(0, 65536) for _ in range(64)]
         for n in ns:
-            assert (n * magic) >> 32 == n // d, (n, d)
+            if n < 65536:                              # the host code only enables the magic for n < 2^16
+                assert (n * magic) >> 32 == n // d, (n, d)

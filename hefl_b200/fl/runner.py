@@ -153,7 +153,7 @@ class FederatedRunner:
     def run_round(self, check: bool = False, pipelined: Optional[bool] = None) -> Dict:
         hist = self.local_train()
         if pipelined is None:
-            pipelined = self.device.type == "cuda" and self.n_ct > 512 and self.transport.name in ("fused", "nccl")
+            pipelined = self.device.type == "cuda" and self.n_ct > 512 and self.transport.name in ("fused", "nccl", "gloo")
         if pipelined:
             self.fedavg_pipelined()
             if self.trainer.engine is not None:

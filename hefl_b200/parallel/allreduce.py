@@ -134,6 +134,8 @@ class CollectiveTransport(Transport):
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.buf = torch.empty(int(max_numel), dtype=torch.int64, device=ctx.device)
+        if dist.is_initialized():
+            self.name = str(dist.get_backend(group))          # "nccl" on GPUs, "gloo" on CPU
 
     def buffer(self, numel: int) -> torch.Tensor:
         return self.buf[:numel]

@@ -9,7 +9,9 @@ process (one process per GPU under ``torchrun``; a single process on CPU or one 
 
 Every ``FLConfig`` field is a flag (``--local-epochs 10``) or an environment variable
 (``HEFL_LOCAL_EPOCHS=10``); the reference hard-codes all of them (FLPyfhelin.py:31-36, notebook N:24-32).
-Extra flags: ``--checkpoint PATH`` (written by rank 0 after every round, resumed from if it exists),
+Extra flags: ``--data-dir DIR`` (the reference's ``image/Train`` layout ``DIR/<label>/<file>``: every rank decodes
+its own IID contiguous shard, 10 % of it validates; without it a synthetic set of the configured shape is used),
+``--checkpoint PATH`` (written by rank 0 after every round, resumed from if it exists),
 ``--simulate`` (all ``--clients`` in this one process through the loopback transport: the reference's own
 structure, clients as loop iterations, FLPyfhelin.py:184).
 """
@@ -31,6 +33,7 @@ def main(argv=None) -> int:
 
     extra = argparse.ArgumentParser(add_help=False)
     extra.add_argument("--checkpoint", default=None)
+    extra.add_argument("--data-dir", default=None)
     extra.add_argument("--simulate", action="store_true")
     extra.add_argument("-h", "--help", action="store_true")
     ns, rest = extra.parse_known_args(argv)
@@ -64,7 +67,14 @@ def main(argv=None) -> int:
         else:
             dist.init_process_group("gloo")
     cfg.clients = world
-    run = FederatedRunner(cfg, rank=rank, world=world, device=device)
+    dataset = None
+    if ns.data_dir:
+        from .fl.data import ImageFolderDataset
+
+        dataset = ImageFolderDataset(ns.data_dir, cfg.image_size, cfg.in_channels, index=rank, num_clients=world,
+                                     shuffle_seed=cfg.seed)
+        cfg.num_classes = max(cfg.num_classes, dataset.classes)
+    run = FederatedRunner(cfg, rank=rank, world=world, device=device, dataset=dataset)
     if ns.checkpoint and os.path.exists(ns.checkpoint):
         run.load_checkpoint(ns.checkpoint)
         if rank == 0:

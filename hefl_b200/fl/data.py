@@ -73,6 +73,66 @@ class SyntheticImageDataset:
         return self.n
 
 
+class ImageFolderDataset:
+    """The reference's image folders (``folder/<label>/<file>``, FLPyfhelin.py:38-55) for the product path:
+    this client's IID contiguous shard (:75-78) is decoded once (PIL, bilinear resize to the model's input
+    size, :104; a thread pool decodes in parallel) into pinned uint8 NHWC memory, from where ``BatchFeeder``
+    streams it to the GPU. Same attributes as ``SyntheticImageDataset``. Class indices come from the sorted
+    label names of the WHOLE folder, so every client agrees on them."""
+
+    def __init__(self, folder: str, image_size: int = 256, channels: int = 3, index: int = 0, num_clients: int = 1,
+                 shuffle_seed: Optional[int] = 0, workers: int = 8, pin: Optional[bool] = None):
+        from concurrent.futures import ThreadPoolExecutor
+
+        df = prep_df(folder, shuffle=shuffle_seed is not None, seed=shuffle_seed)
+        if len(df) == 0:
+            raise FileNotFoundError(f"no images under {folder}/<label>/")
+        names = sorted(set(df["Label"]))
+        self.class_indices = {l: i for i, l in enumerate(names)}
+        lo, hi = shard_range(len(df), index, num_clients)
+        rows = df.iloc[lo:hi]
+        self.filenames = list(rows["Path"])
+        n = len(self.filenames)
+        imgs = torch.zeros(n, image_size, image_size, channels, dtype=torch.uint8)
+
+        def load(i: int) -> None:
+            imgs[i] = torch.from_numpy(np.ascontiguousarray(_decode(self.filenames[i], image_size, channels)))
+
+        with ThreadPoolExecutor(max_workers=max(1, workers)) as ex:
+            list(ex.map(load, range(n)))
+        labels = torch.tensor([self.class_indices[l] for l in rows["Label"]], dtype=torch.int64)
+        pin = torch.cuda.is_available() if pin is None else pin
+        self.images = imgs.pin_memory() if pin else imgs
+        self.labels = labels.pin_memory() if pin else labels
+        self.n = n
+        self.classes = len(names)
+
+    def __len__(self) -> int:
+        return self.n
+
+
+def _decode(path: str, size: int, channels: int) -> np.ndarray:
+    """uint8 [size, size, channels] from an image file (or a .npy array), bilinear resize."""
+    if path.endswith(".npy"):
+        arr = np.load(path)
+        if arr.ndim == 2:
+            arr = arr[:, :, None]
+        if arr.shape[0] != size or arr.shape[1] != size:
+            t = torch.from_numpy(arr).permute(2, 0, 1)[None].float()
+            t = torch.nn.functional.interpolate(t, size=(size, size), mode="bilinear", align_corners=False)
+            arr = t[0].permute(1, 2, 0).round().clamp(0, 255).to(torch.uint8).numpy()
+    else:
+        from PIL import Image
+
+        img = Image.open(path).convert("RGB" if channels == 3 else "L").resize((size, size), Image.BILINEAR)
+        arr = np.asarray(img)
+        if arr.ndim == 2:
+            arr = arr[:, :, None]
+    if arr.shape[2] != channels:
+        arr = arr[:, :, :1].repeat(channels, axis=2) if arr.shape[2] == 1 else arr[:, :, :channels]
+    return arr.astype(np.uint8)
+
+
 class BatchFeeder:
     """Fixed-size batches over an index range. On CUDA every step's images go host->device
     straight from the pinned dataset (one async copy per row, issued by the native

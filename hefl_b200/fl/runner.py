@@ -36,7 +36,7 @@ from .trainer import LocalTrainer
 
 class FederatedRunner:
     def __init__(self, cfg: FLConfig, rank: int = 0, world: int = 1, group=None,
-                 device: Optional[torch.device] = None, samples_per_client: Optional[int] = None):
+                 device: Optional[torch.device] = None, samples_per_client: Optional[int] = None, dataset=None):
         self.cfg = cfg
         self.rank, self.world, self.group = rank, world, group
         self.device = device or torch.device(cfg.device if torch.cuda.is_available() or cfg.device == "cpu" else "cpu")
@@ -57,10 +57,16 @@ class FederatedRunner:
                                         **({"algo": cfg.allreduce_algo, "timeout_s": cfg.timeout_s}
                                            if kind == "fused" else {}))
         # data: IID contiguous shard of a synthetic set (FLPyfhelin.py:75-78), 90/10 split (:85)
-        per = samples_per_client or (cfg.steps_per_epoch * cfg.batch_size + cfg.val_steps * cfg.batch_size)
-        self.dataset = SyntheticImageDataset(per, cfg.image_size, cfg.in_channels, cfg.num_classes,
-                                             seed=cfg.seed + 17 * rank)
-        nval = cfg.val_steps * cfg.batch_size
+        # or, with ``dataset`` (e.g. ImageFolderDataset of this client's shard), real images: 10 % validate
+        if dataset is not None:
+            self.dataset = dataset
+            per = len(dataset)
+            nval = int(per * 0.1)
+        else:
+            per = samples_per_client or (cfg.steps_per_epoch * cfg.batch_size + cfg.val_steps * cfg.batch_size)
+            self.dataset = SyntheticImageDataset(per, cfg.image_size, cfg.in_channels, cfg.num_classes,
+                                                 seed=cfg.seed + 17 * rank)
+            nval = cfg.val_steps * cfg.batch_size
         self.train_feed = BatchFeeder(self.dataset, range(nval, per), cfg.batch_size, self.device,
                                       shuffle=True, seed=cfg.seed + rank)
         self.val_feed = BatchFeeder(self.dataset, range(0, nval), cfg.batch_size, self.device,

@@ -39,3 +39,42 @@ def test_cli_env_overrides_and_simulation_mode():
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert d["mode"] == "simulate" and d["clients"] == 3 and d["max_abs_err_vs_plaintext"] < 1e-4
+
+
+def test_cli_trains_on_an_image_folder(tmp_path):
+    """--data-dir: the reference's folder layout (<dir>/<label>/<file>), decoded by the threaded loader."""
+    import numpy as np
+    from PIL import Image
+    rng = np.random.default_rng(0)
+    for label in ("NORMAL", "PNEUMONIA"):
+        d = tmp_path / "Train" / label
+        d.mkdir(parents=True)
+        for i in range(20):
+            img = rng.integers(0, 120, (20, 24, 3), dtype=np.uint8)        # not the model's size: resized on load
+            if label == "PNEUMONIA":
+                img[:8, :8] += 100
+            Image.fromarray(img).save(d / f"{i:03d}.png")
+    args = ["--device", "cpu", "--model", "cnn2", "--image-size", "28", "--in-channels", "3", "--num-classes", "2",
+            "--batch-size", "8", "--local-epochs", "2", "--he-preset", "n2048_l1", "--nn-backend", "cudnn",
+            "--dtype", "fp32", "--rounds", "1", "--data-dir", str(tmp_path / "Train")]
+    r = _run(args)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["round"] == 0 and d["loss"] == d["loss"]
+
+
+def test_image_folder_dataset_shards_like_the_reference(tmp_path):
+    import numpy as np
+    from PIL import Image
+    from hefl_b200.fl.data import ImageFolderDataset
+    for label in ("a", "b", "c"):
+        d = tmp_path / label
+        d.mkdir()
+        for i in range(7):
+            Image.fromarray(np.full((9, 9, 3), 10 * i, dtype=np.uint8)).save(d / f"{i}.png")
+    full = ImageFolderDataset(str(tmp_path), image_size=8, shuffle_seed=3, pin=False)
+    assert len(full) == 21 and full.classes == 3 and full.images.shape == (21, 8, 8, 3)
+    parts = [ImageFolderDataset(str(tmp_path), image_size=8, index=i, num_clients=2, shuffle_seed=3, pin=False) for i in range(2)]
+    assert [len(p) for p in parts] == [10, 10]                       # int(21 / 2) each, remainder dropped (F:75-78)
+    assert parts[0].filenames + parts[1].filenames == full.filenames[:20]
+    assert parts[0].class_indices == parts[1].class_indices == {"a": 0, "b": 1, "c": 2}

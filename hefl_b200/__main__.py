@@ -11,6 +11,8 @@ Every ``FLConfig`` field is a flag (``--local-epochs 10``) or an environment var
 (``HEFL_LOCAL_EPOCHS=10``); the reference hard-codes all of them (FLPyfhelin.py:31-36, notebook N:24-32).
 Extra flags: ``--data-dir DIR`` (the reference's ``image/Train`` layout ``DIR/<label>/<file>``: every rank decodes
 its own IID contiguous shard, 10 % of it validates; without it a synthetic set of the configured shape is used),
+``--test-dir DIR`` (same layout; after the last round rank 0 prints the reference's four metrics — weighted
+precision / recall / F1 and accuracy, notebook N:267-270 — of the aggregated model),
 ``--checkpoint PATH`` (written by rank 0 after every round, resumed from if it exists),
 ``--simulate`` (all ``--clients`` in this one process through the loopback transport: the reference's own
 structure, clients as loop iterations, FLPyfhelin.py:184).
@@ -34,6 +36,7 @@ def main(argv=None) -> int:
     extra = argparse.ArgumentParser(add_help=False)
     extra.add_argument("--checkpoint", default=None)
     extra.add_argument("--data-dir", default=None)
+    extra.add_argument("--test-dir", default=None)
     extra.add_argument("--simulate", action="store_true")
     extra.add_argument("-h", "--help", action="store_true")
     ns, rest = extra.parse_known_args(argv)
@@ -90,7 +93,13 @@ def main(argv=None) -> int:
                 run.save_checkpoint(ns.checkpoint)
         if world > 1:
             dist.barrier()
+    if ns.test_dir and rank == 0:
+        from .fl.data import ImageFolderDataset
+
+        test = ImageFolderDataset(ns.test_dir, cfg.image_size, cfg.in_channels, shuffle_seed=None, pin=False)
+        print(json.dumps({"test_images": len(test), **run.evaluate(test)}))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

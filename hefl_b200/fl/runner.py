@@ -205,6 +205,22 @@ class FederatedRunner:
             out.append(rec)
         return out
 
+    # ------------------------------------------------------------------ evaluation (notebook N:262-270)
+    @torch.no_grad()
+    def evaluate(self, dataset, batch_size: Optional[int] = None) -> Dict[str, float]:
+        """Weighted precision / recall / F1 and accuracy of the current global model on ``dataset`` — the four
+        numbers the reference's notebook reports after aggregation (sklearn ``average='weighted'``, N:267-270).
+        Runs the plain PyTorch forward of the model (any backend / device); not a hot path."""
+        bs = batch_size or self.cfg.batch_size
+        self.model.eval()
+        preds = []
+        for i in range(0, len(dataset), bs):
+            x = dataset.images[i:i + bs].to(self.device, non_blocking=True)
+            x = x.permute(0, 3, 1, 2).float() * (1.0 / 255.0)
+            preds.append(self.model(x).float().argmax(1).cpu())
+        self.model.train()
+        return classification_metrics(dataset.labels.cpu(), torch.cat(preds), int(getattr(dataset, "classes", self.cfg.num_classes)))
+
     # ------------------------------------------------------------------ checkpoint / resume
     def save_checkpoint(self, path: str) -> None:
         """Round index + model + optimiser + RNG so multi-round runs resume."""
@@ -223,6 +239,25 @@ class FederatedRunner:
             torch.cuda.set_rng_state(ck["cuda_rng"], self.device)
         if self.trainer.engine is not None:
             self.trainer.engine.after_restore()
+
+
+def classification_metrics(y_true: torch.Tensor, y_pred: torch.Tensor, num_classes: int) -> Dict[str, float]:
+    """precision / recall / f1 (support-weighted, zero where undefined — sklearn's ``average='weighted',
+    zero_division=0``) and accuracy."""
+    y_true, y_pred = y_true.long().flatten(), y_pred.long().flatten()
+    n = max(1, y_true.numel())
+    num_classes = max(num_classes, int(max(y_true.max(), y_pred.max())) + 1) if y_true.numel() else num_classes
+    p_w = r_w = f_w = 0.0
+    for c in range(num_classes):
+        tp = float(((y_pred == c) & (y_true == c)).sum())
+        fp = float(((y_pred == c) & (y_true != c)).sum())
+        fn = float(((y_pred != c) & (y_true == c)).sum())
+        prec = tp / (tp + fp) if tp + fp > 0 else 0.0
+        rec = tp / (tp + fn) if tp + fn > 0 else 0.0
+        f1 = 2 * prec * rec / (prec + rec) if prec + rec > 0 else 0.0
+        w = (tp + fn) / n
+        p_w, r_w, f_w = p_w + w * prec, r_w + w * rec, f_w + w * f1
+    return {"precision": p_w, "recall": r_w, "f1": f_w, "accuracy": float((y_true == y_pred).sum()) / n}
 
 
 def simulate_clients(cfg: FLConfig, device: Optional[torch.device] = None, rounds: int = 1,

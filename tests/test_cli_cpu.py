@@ -56,11 +56,13 @@ def test_cli_trains_on_an_image_folder(tmp_path):
             Image.fromarray(img).save(d / f"{i:03d}.png")
     args = ["--device", "cpu", "--model", "cnn2", "--image-size", "28", "--in-channels", "3", "--num-classes", "2",
             "--batch-size", "8", "--local-epochs", "2", "--he-preset", "n2048_l1", "--nn-backend", "cudnn",
-            "--dtype", "fp32", "--rounds", "1", "--data-dir", str(tmp_path / "Train")]
+            "--dtype", "fp32", "--rounds", "1", "--data-dir", str(tmp_path / "Train"), "--test-dir", str(tmp_path / "Train")]
     r = _run(args)
     assert r.returncode == 0, r.stderr[-2000:]
-    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
-    assert d["round"] == 0 and d["loss"] == d["loss"]
+    recs = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    assert recs[0]["round"] == 0 and recs[0]["loss"] == recs[0]["loss"]
+    m = recs[-1]
+    assert m["test_images"] == 40 and all(0.0 <= m[k] <= 1.0 for k in ("precision", "recall", "f1", "accuracy"))
 
 
 def test_image_folder_dataset_shards_like_the_reference(tmp_path):
@@ -78,3 +80,21 @@ def test_image_folder_dataset_shards_like_the_reference(tmp_path):
     assert [len(p) for p in parts] == [10, 10]                       # int(21 / 2) each, remainder dropped (F:75-78)
     assert parts[0].filenames + parts[1].filenames == full.filenames[:20]
     assert parts[0].class_indices == parts[1].class_indices == {"a": 0, "b": 1, "c": 2}
+
+
+def test_classification_metrics_match_sklearn_weighted():
+    import numpy as np
+    import torch
+    from sklearn.metrics import accuracy_score, f1_score, precision_score, recall_score
+    from hefl_b200.fl import classification_metrics
+    rng = np.random.default_rng(1)
+    for k in (2, 3, 5):
+        yt = rng.integers(0, k, 200); yp = rng.integers(0, k, 200)
+        yp[:40] = yt[:40]
+        if k == 5:
+            yp[yp == 4] = 0                                   # a class that is never predicted (zero_division path)
+        m = classification_metrics(torch.from_numpy(yt), torch.from_numpy(yp), k)
+        assert abs(m["precision"] - precision_score(yt, yp, average="weighted", zero_division=0)) < 1e-9
+        assert abs(m["recall"] - recall_score(yt, yp, average="weighted", zero_division=0)) < 1e-9
+        assert abs(m["f1"] - f1_score(yt, yp, average="weighted", zero_division=0)) < 1e-9
+        assert abs(m["accuracy"] - accuracy_score(yt, yp)) < 1e-12

@@ -48,6 +48,15 @@ class FederatedRunner:
         self.ctx = CKKSContext(hp["n"], prime_bits=hp["prime_bits"], scale_bits=hp["scale_bits"],
                                device=self.device, sec=cfg.sec)
         self.sk, self.pk = self.ctx.keygen(seed=cfg.seed)   # same seed on every rank -> same keys
+        # trust model: by default every client can decrypt the aggregate (nobody ever sees another client's
+        # plaintext update: the transport only carries ciphertext sums). With ``key_holder = r`` only rank r
+        # keeps the secret key, decrypts, and broadcasts the averaged plaintext model.
+        self.key_holder = int(cfg.key_holder) if world > 1 else -1
+        if self.key_holder >= world:
+            raise ValueError(f"key_holder {self.key_holder} is not a rank of this {world}-client federation")
+        self.has_sk = self.key_holder < 0 or rank == self.key_holder
+        if not self.has_sk:
+            self.sk = None
         self.n_ct = self.ctx.num_ct(self.pack.numel, cfg.packing)
         self.ct_numel = self.n_ct * 2 * self.ctx.L * self.ctx.n
         kind = cfg.transport
@@ -97,7 +106,13 @@ class FederatedRunner:
     def decrypt_apply(self, agg: CtBatch) -> None:
         with self.timer.stage("decrypt"):
             k = self.transport.contributors()
-            avg = self.ctx.decrypt(agg, self.sk, divide_by=float(k))
+            if self.has_sk:
+                avg = self.ctx.decrypt(agg, self.sk, divide_by=float(k))
+            else:
+                avg = torch.empty_like(self.pack.flat)
+            if self.key_holder >= 0:
+                avg = avg.to(self.pack.flat.dtype).contiguous()
+                dist.broadcast(avg, src=self.key_holder, group=self.group)
             self.pack.load_flat(avg)
             if self.trainer.engine is not None:
                 self.trainer.engine.after_restore()
@@ -143,11 +158,14 @@ class FederatedRunner:
                 with torch.cuda.stream(s_dec):
                     s_dec.wait_event(ev_comm[ci])
                     from ..he.context import CtBatch as _CB
-                    avg = ctx.decrypt(_CB(data, ct.scale, ct.nvals, ct.packing), self.sk, divide_by=k)
-                    out[c0 * vpc: c0 * vpc + avg.numel()].copy_(avg)
+                    if self.has_sk:
+                        avg = ctx.decrypt(_CB(data, ct.scale, ct.nvals, ct.packing), self.sk, divide_by=k)
+                        out[c0 * vpc: c0 * vpc + avg.numel()].copy_(avg)
             cur.wait_stream(s_dec)
             cur.wait_stream(s_comm)
             cur.wait_stream(s_enc)
+            if self.key_holder >= 0:
+                dist.broadcast(out, src=self.key_holder, group=self.group)
             self.pack.load_flat(out)
 
     def guard_finite(self) -> None:

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--model", default="cnn2")
     ap.add_argument("--transport", default=None)
     ap.add_argument("--rounds", type=int, default=2)
+    ap.add_argument("--key-holder", type=int, default=-1)
     args = ap.parse_args()
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
     gpu = args.backend == "nccl"
@@ -39,7 +40,10 @@ def main():
                        steps_per_epoch=2, val_steps=1, clients=world, he_preset="n4096_l3", nn_backend="cudnn",
                        dtype="bf16" if gpu else "fp32", transport=args.transport or ("fused" if gpu else "gloo"),
                        device="cuda" if gpu else "cpu", debug_poison=True)   # stale words would break the cross-check
+    cfg.key_holder = args.key_holder
     run = FederatedRunner(cfg, rank=rank, world=world, device=device)
+    if args.key_holder >= 0:
+        assert (run.sk is not None) == (rank == args.key_holder), "only the key holder may keep the secret key"
     worst = 0.0
     for rnd in range(args.rounds):
         run.local_train()

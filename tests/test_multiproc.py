@@ -46,6 +46,12 @@ def test_federated_round_gloo_world2():
     assert rep["world"] == 2 and rep["max_abs_err"] < 1e-5
 
 
+def test_federated_round_with_a_single_key_holder_gloo():
+    """key_holder=1: only rank 1 keeps the secret key, decrypts and broadcasts; same result on every rank."""
+    rep = _run(2, "gloo", 29643, ["--rounds", "2", "--key-holder", "1"], worker=FED_WORKER)
+    assert rep["world"] == 2 and rep["max_abs_err"] < 1e-5
+
+
 @pytest.mark.gpu
 @pytest.mark.multigpu
 @pytest.mark.parametrize("nproc,model", [(2, "cnn2"), (2, "medcnn"), (8, "medcnn")])

@@ -62,10 +62,9 @@ class LocalTrainer:
         # "fp8": bf16 autocast + e4m3 GEMMs for the 1x1 convolutions of the ResNets (ops/fp8.py)
         self.amp_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32,
                           "fp8": torch.bfloat16}[cfg.dtype]
-        if cfg.dtype == "fp8":
-            from ..ops import fp8 as _fp8
+        from ..ops import fp8 as _fp8
 
-            _fp8.ENABLE = self.cuda
+        _fp8.set_model_fp8(model, cfg.dtype == "fp8" and self.cuda)      # per model, not process-wide
         B, S, C = cfg.batch_size, cfg.image_size, cfg.in_channels
         self.static_x = torch.zeros(B, S, S, C, dtype=torch.uint8, device=device)
         self.static_y = torch.zeros(B, dtype=torch.int64, device=device)

@@ -4,8 +4,8 @@ operands are quantised by the hand-written one-pass kernel ``fp8_quantize`` (sca
 step's amax, this step's amax recorded for the next — csrc/nn/resnet_kernels.cu) and multiplied by the
 library fp8 GEMM (cuBLASLt through ``torch._scaled_mm``); gradients stay in bf16.
 
-Off by default; ``FLConfig(dtype="fp8")`` turns it on for the ResNets (everything else — 3x3/7x7
-convolutions, BatchNorm, the head — runs in bf16)."""
+Off by default; ``FLConfig(dtype="fp8")`` turns it on per model (``set_model_fp8``) for the ResNets
+(everything else — 3x3/7x7 convolutions, BatchNorm, the head — runs in bf16)."""
 from __future__ import annotations
 
 import torch
@@ -16,6 +16,16 @@ from .. import _ext
 ENABLE = False
 E4M3_MAX = 448.0
 MARGIN = 2.0            # head-room for values that grow between two steps (delayed scaling)
+
+
+def set_model_fp8(model: nn.Module, on: bool) -> int:
+    """Switch every ``Conv1x1`` of ``model`` to fp8 (or back); returns how many there are."""
+    n = 0
+    for m in model.modules():
+        if isinstance(m, Conv1x1):
+            m.use_fp8 = bool(on)
+            n += 1
+    return n
 
 
 class DelayedScale:
@@ -76,9 +86,11 @@ class Conv1x1(nn.Conv2d):
     def __init__(self, cin: int, cout: int, stride: int = 1):
         super().__init__(cin, cout, 1, stride, 0, bias=False)
         self._fp8_state = None
+        self.use_fp8 = None          # None: follow the module-level ENABLE; True / False: per-model choice (trainer)
 
     def forward(self, x):
-        ok = (ENABLE and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4
+        on = ENABLE if self.use_fp8 is None else self.use_fp8
+        ok = (on and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4
               and self.in_channels % 16 == 0 and self.out_channels % 16 == 0)
         if not ok:
             return super().forward(x)

@@ -84,3 +84,22 @@ def test_debug_poison_between_rounds_keeps_results_identical():
     b, nb, rb = run(True)
     assert na == 0 and nb == 2
     assert torch.equal(a, b)
+
+
+def test_fp8_flag_is_per_model_not_process_wide():
+    """FLConfig(dtype="fp8") marks the 1x1 convolutions of THAT model; another trainer in the same process
+    (bf16) is not affected, and on CPU the flag stays off (the fp8 GEMM path is CUDA-only)."""
+    import torch
+    from hefl_b200.fl.trainer import LocalTrainer
+    from hefl_b200.models import ParamPack, create_model
+    from hefl_b200.ops import fp8
+
+    m = create_model("resnet50", num_classes=4)
+    assert fp8.set_model_fp8(m, True) >= 30 and all(c.use_fp8 for c in m.modules() if isinstance(c, fp8.Conv1x1))
+    cfg = _cfg(model="resnet18", image_size=32, in_channels=3, num_classes=4, dtype="fp32")
+    net = create_model("resnet18", in_channels=3, num_classes=4)
+    LocalTrainer(net, ParamPack(net), cfg, torch.device("cpu"))
+    assert all(c.use_fp8 is False for c in net.modules() if isinstance(c, fp8.Conv1x1))
+    assert fp8.ENABLE is False
+    x = torch.randn(2, 3, 32, 32)
+    assert net(x).shape == (2, 4)                 # fallback path is a plain convolution

@@ -746,6 +746,10 @@ void conv_fwd_pool_pair(const void* X, const void* Wf, const float* bias, void* 
 // Split over (image, strip, row range); fp32 vector-RED of the partial sums into a [9*C+1, Co]
 // buffer whose last row is the bias gradient (an all-ones A tile).
 // ------------------------------------------------------------------------------------------
+#ifndef HEFL_WGRAD_OCC3
+#define HEFL_WGRAD_OCC3 0     // 1: allow three wgrad CTAs per SM (validated build flag, see WgradCfg::OCC)
+#endif
+
 struct WgradArgs {
   int H, W, Ho;     // input grid height/width, valid output rows
   int strips;       // ceil((W-2) / 64)
@@ -791,7 +795,10 @@ struct WgradCfg {
   static_assert(NSTAGE >= 4, "ring needs 3 live stages + 1 in flight");
   static constexpr int TMEM_COLS = COLS <= 32 ? 32 : (COLS <= 64 ? 64 : (COLS <= 128 ? 128 : (COLS <= 256 ? 256 : 512)));
   static_assert(COLS <= 512, "accumulators exceed TMEM");
-  static constexpr int OCC = (2 * SMEM <= 226 * 1024 && 2 * TMEM_COLS <= 512) ? 2 : 1;   // CTAs per SM
+  // CTAs per SM. ncu (prof_wgrad1): 22 % tensor-pipe active, 7 % issue active, occupancy limit 3 by shared memory
+  // while 2 were launched — the kernel is latency-bound, so take the third CTA when smem and TMEM allow it.
+  static constexpr int OCC = (HEFL_WGRAD_OCC3 && 3 * SMEM <= 226 * 1024 && 3 * TMEM_COLS <= 512) ? 3
+                             : ((2 * SMEM <= 226 * 1024 && 2 * TMEM_COLS <= 512) ? 2 : 1);
   static_assert(CK == 16 || CK == 32 || CK == 64, "CK must be one swizzle atom");
   static_assert(COT == 32 || COT == 64, "COT must be one swizzle atom");
 };

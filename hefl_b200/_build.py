@@ -34,7 +34,7 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
-]
+] + os.environ.get("HEFL_NVCC_EXTRA", "").split()      # e.g. HEFL_NVCC_EXTRA="-DHEFL_WGRAD_OCC3=1" (experiments)
 
 CUDA_SOURCES = [
     "he/cuda/he_kernels.cu",

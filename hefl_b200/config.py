@@ -56,6 +56,8 @@ class FLConfig:
     compat_sequential_clients: bool = False   # reproduce quirk Q1 (FLPyfhelin.py:180-193)
     key_holder: int = -1                      # -1: every client holds the secret key (the reference's notebook owns
                                               # privatekey.pickle); r >= 0: only rank r decrypts and broadcasts the average
+    debug_precision: bool = False             # also all-reduce the PLAINTEXT updates and record the CKKS error of the
+                                              # round (debug only: it defeats the privacy the ciphertext path provides)
     debug_poison: bool = False                # overwrite ciphertext / scratch buffers with a poison pattern between rounds
     # HE
     he_preset: str = "n4096_l3"

@@ -176,6 +176,13 @@ class FederatedRunner:
     # ------------------------------------------------------------------ round
     def run_round(self, check: bool = False, pipelined: Optional[bool] = None) -> Dict:
         hist = self.local_train()
+        plain_mean = None
+        if self.cfg.debug_precision and not isinstance(self.transport, LoopbackTransport):
+            # plaintext FedAvg oracle (SURVEY.md §5.5 "CKKS precision: max abs error vs plaintext FedAvg")
+            plain_mean = self.pack.flat.detach().clone().double()
+            if self.world > 1:
+                dist.all_reduce(plain_mean, op=dist.ReduceOp.SUM, group=self.group)
+                plain_mean /= self.world
         if pipelined is None:
             pipelined = self.device.type == "cuda" and self.n_ct > 512 and self.transport.name in ("fused", "nccl", "gloo")
         if pipelined:
@@ -196,6 +203,10 @@ class FederatedRunner:
         rec = {"round": self.round, "rank": self.rank, "stage_ms": times,
                "loss": hist[-1].loss if hist else None, "accuracy": hist[-1].accuracy if hist else None,
                "transport": self.transport.name, "n_ct": self.n_ct, "ct_bytes": self.ct_numel * 8}
+        if plain_mean is not None:
+            err = float((self.pack.flat.double() - plain_mean).abs().max())
+            rec["ckks_max_abs_err"] = err
+            rec["ckks_precision_bits"] = float(-math.log2(err)) if err > 0 else float("inf")
         self.history.append(rec)
         self.round += 1
         return rec

@@ -103,3 +103,15 @@ def test_fp8_flag_is_per_model_not_process_wide():
     assert fp8.ENABLE is False
     x = torch.randn(2, 3, 32, 32)
     assert net(x).shape == (2, 4)                 # fallback path is a plain convolution
+
+
+def test_round_record_reports_ckks_precision_when_asked():
+    import torch
+    from hefl_b200.fl import FederatedRunner
+    cfg = _cfg(local_epochs=1, steps_per_epoch=2, clients=1, transport="gloo", debug_precision=True)
+    r = FederatedRunner(cfg, device=torch.device("cpu"))
+    rec = r.run_round(check=True)
+    assert rec["ckks_max_abs_err"] < 1e-6 and rec["ckks_precision_bits"] > 20
+    cfg2 = _cfg(local_epochs=1, steps_per_epoch=2, clients=1, transport="gloo")
+    rec2 = FederatedRunner(cfg2, device=torch.device("cpu")).run_round()
+    assert "ckks_max_abs_err" not in rec2

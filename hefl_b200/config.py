@@ -56,6 +56,8 @@ class FLConfig:
     compat_sequential_clients: bool = False   # reproduce quirk Q1 (FLPyfhelin.py:180-193)
     key_holder: int = -1                      # -1: every client holds the secret key (the reference's notebook owns
                                               # privatekey.pickle); r >= 0: only rank r decrypts and broadcasts the average
+    allow_dropouts: bool = False              # clients may sit a round out (participation mask): K becomes a runtime
+                                              # value agreed by a 1-element all-reduce and folded into the decode scale
     debug_precision: bool = False             # also all-reduce the PLAINTEXT updates and record the CKKS error of the
                                               # round (debug only: it defeats the privacy the ciphertext path provides)
     debug_poison: bool = False                # overwrite ciphertext / scratch buffers with a poison pattern between rounds

@@ -81,6 +81,8 @@ class FederatedRunner:
         self.val_feed = BatchFeeder(self.dataset, range(0, nval), cfg.batch_size, self.device,
                                     shuffle=True, seed=cfg.seed + rank) if nval else None
         self.round = 0
+        self.participating = True        # set False to sit a round out (needs cfg.allow_dropouts on every rank)
+        self._active = None              # contributors of the current round when dropouts are allowed
         self.timer = DeviceTimer(self.device)
         self.log = JsonlLogger(cfg.log_jsonl, rank)
         self.global_flat = self.pack.flat.clone()
@@ -92,11 +94,32 @@ class FederatedRunner:
             return self.trainer.fit(self.train_feed, self.val_feed, self.cfg.local_epochs,
                                     early_stopping=early_stopping)
 
+    def _contributors(self) -> float:
+        """K of this round: the world size, or — with ``allow_dropouts`` — the number of ranks that take part
+        (participation mask). A client that sits out still joins the collective with an
+        encryption of zeros, so the fused kernel and its barriers are unchanged."""
+        if self._active is not None:
+            return float(self._active)
+        return float(self.transport.contributors())
+
+    def _agree_on_participants(self) -> None:
+        self._active = None
+        if not self.cfg.allow_dropouts or isinstance(self.transport, LoopbackTransport):
+            return
+        t = torch.tensor([1.0 if self.participating else 0.0], dtype=torch.float32, device=self.device)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        self._active = int(round(float(t)))
+
+    def _my_update(self) -> torch.Tensor:
+        return self.pack.flat if (self.participating or not self.cfg.allow_dropouts) else torch.zeros_like(self.pack.flat)
+
     def encrypt_update(self) -> CtBatch:
+        self._agree_on_participants()
         with self.timer.stage("encrypt"):
             buf = self.transport.buffer(self.ct_numel)
             seed = (self.cfg.seed * 1_000_003 + self.round * 1009 + self.rank) & 0x7FFFFFFFFFFFFFFF
-            return self.ctx.encrypt(self.pack.flat, self.pk, seed=seed, packing=self.cfg.packing, out=buf)
+            return self.ctx.encrypt(self._my_update(), self.pk, seed=seed, packing=self.cfg.packing, out=buf)
 
     def aggregate(self, ct: CtBatch) -> CtBatch:
         with self.timer.stage("aggregate"):
@@ -105,7 +128,9 @@ class FederatedRunner:
 
     def decrypt_apply(self, agg: CtBatch) -> None:
         with self.timer.stage("decrypt"):
-            k = self.transport.contributors()
+            k = self._contributors()
+            if k == 0:                                       # nobody took part: keep the current global model
+                return
             if self.has_sk:
                 avg = self.ctx.decrypt(agg, self.sk, divide_by=float(k))
             else:
@@ -127,9 +152,12 @@ class FederatedRunner:
         vpc = ctx.values_per_ct(self.cfg.packing)
         n_ct = self.n_ct
         per_ct = 2 * ctx.L * ctx.n
-        flat = self.pack.flat
+        self._agree_on_participants()
+        flat = self._my_update()
         out = torch.empty_like(flat)
-        k = float(self.transport.contributors())
+        k = self._contributors()
+        if k == 0:
+            return
         seed = (self.cfg.seed * 1_000_003 + self.round * 1009 + self.rank) & 0x7FFFFFFFFFFFFFFF
         # the three streams live as long as the runner: the caching allocator keeps one pool per stream, so
         # fresh streams every round meant fresh cudaMallocs (and cudaFree stalls) every round

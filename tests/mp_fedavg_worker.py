@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--transport", default=None)
     ap.add_argument("--rounds", type=int, default=2)
     ap.add_argument("--key-holder", type=int, default=-1)
+    ap.add_argument("--drop-rank", type=int, default=-1)
     args = ap.parse_args()
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
     gpu = args.backend == "nccl"
@@ -41,6 +42,7 @@ def main():
                        dtype="bf16" if gpu else "fp32", transport=args.transport or ("fused" if gpu else "gloo"),
                        device="cuda" if gpu else "cpu", debug_poison=True)   # stale words would break the cross-check
     cfg.key_holder = args.key_holder
+    cfg.allow_dropouts = args.drop_rank >= 0
     run = FederatedRunner(cfg, rank=rank, world=world, device=device)
     if args.key_holder >= 0:
         assert (run.sk is not None) == (rank == args.key_holder), "only the key holder may keep the secret key"
@@ -50,6 +52,9 @@ def main():
         mine = run.pack.flat.clone()
         gathered = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine)
+        if args.drop_rank >= 0:                       # that client sits every round out: mean over the others
+            run.participating = rank != args.drop_rank
+            gathered = [g for r, g in enumerate(gathered) if r != args.drop_rank]
         plain_mean = torch.stack(gathered).mean(0)
         ct = run.encrypt_update()
         agg = run.aggregate(ct)

@@ -46,6 +46,13 @@ def test_federated_round_gloo_world2():
     assert rep["world"] == 2 and rep["max_abs_err"] < 1e-5
 
 
+def test_federated_round_with_a_dropped_client_gloo():
+    """allow_dropouts: rank 1 sits the rounds out (encrypts zeros); K = 1 is agreed at run time and the
+    aggregate equals the mean over the participating clients on every rank."""
+    rep = _run(2, "gloo", 29645, ["--rounds", "2", "--drop-rank", "1"], worker=FED_WORKER)
+    assert rep["world"] == 2 and rep["max_abs_err"] < 1e-5
+
+
 def test_federated_round_with_a_single_key_holder_gloo():
     """key_holder=1: only rank 1 keeps the secret key, decrypts and broadcasts; same result on every rank."""
     rep = _run(2, "gloo", 29643, ["--rounds", "2", "--key-holder", "1"], worker=FED_WORKER)

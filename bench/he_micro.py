@@ -1,5 +1,6 @@
 """Micro-benchmark of the HE kernels on one GPU (CUDA events, warm-up, L2 flush between
-iterations). Writes gpurun_out/he_micro.json."""
+iterations). Writes gpurun_out/he_micro_v2.json (persistent TMA/cluster kernels, the default) or,
+with HEFL_HE_V1=1, gpurun_out/he_micro_v1.json (the first-generation kernels) for an A/B."""
 import json
 import os
 import sys
@@ -71,7 +72,9 @@ def main():
         del ct, res, msg, vals
         torch.cuda.empty_cache()
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(out, open("gpurun_out/he_micro.json", "w"), indent=1)
+    tag = "v1" if os.environ.get("HEFL_HE_V1") == "1" else "v2"
+    out["kernels"] = tag
+    json.dump(out, open(f"gpurun_out/he_micro_{tag}.json", "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -462,7 +462,6 @@ encrypt_kernel(const int64_t* __restrict__ msg, const uint64_t* __restrict__ pk,
   const Modulus m{T.q, T.ratio_lo, T.ratio_hi};
   uint64_t* bufA = smem;
   uint64_t* bufU = TWO_BUF ? smem + padded_len(n) : smem;
-  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   const uint32_t cid = ct_offset + (uint32_t)c;
   uint64_t* c0 = ct + ((c * 2 + 0) * L + l) * n;
   uint64_t* c1 = ct + ((c * 2 + 1) * L + l) * n;
@@ -472,8 +471,7 @@ encrypt_kernel(const int64_t* __restrict__ msg, const uint64_t* __restrict__ pk,
 
   // pass 1: u
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const Philox4 a = philox4x32_10((uint32_t)i, cid, 0u, STREAM_ENC_A, k0, k1);
-    bufU[pad_idx(i)] = lift_signed(ternary_from(a.x), T.q);
+    bufU[pad_idx(i)] = lift_signed(sample_enc_noise(seed, cid, (uint32_t)i).u, T.q);
   }
   ntt_fwd_block(bufU, logn, logn, 0, T);
   if (!TWO_BUF) {
@@ -486,10 +484,9 @@ encrypt_kernel(const int64_t* __restrict__ msg, const uint64_t* __restrict__ pk,
   }
   // pass 2: e0 + scale*m
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const Philox4 a = philox4x32_10((uint32_t)i, cid, 0u, STREAM_ENC_A, k0, k1);
     uint64_t mm = msg ? reduce_signed(msg[c * n + i], m) : 0;
     if (sc != 1) mm = mul_mod(mm, sc, m);
-    bufA[pad_idx(i)] = add_mod(lift_signed(cbd21_from(a.y, a.z), T.q), mm, T.q);
+    bufA[pad_idx(i)] = add_mod(lift_signed(sample_enc_noise(seed, cid, (uint32_t)i).e0, T.q), mm, T.q);
   }
   ntt_fwd_block(bufA, logn, logn, 0, T);
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -504,8 +501,7 @@ encrypt_kernel(const int64_t* __restrict__ msg, const uint64_t* __restrict__ pk,
   __syncthreads();
   // pass 3: e1
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const Philox4 b = philox4x32_10((uint32_t)i, cid, 0u, STREAM_ENC_B, k0, k1);
-    bufA[pad_idx(i)] = lift_signed(cbd21_from(b.x, b.y), T.q);
+    bufA[pad_idx(i)] = lift_signed(sample_enc_noise(seed, cid, (uint32_t)i).e1, T.q);
   }
   ntt_fwd_block(bufA, logn, logn, 0, T);
   for (int i = threadIdx.x; i < n; i += blockDim.x) {

@@ -5,6 +5,10 @@
 #include <torch/library.h>
 #include <torch/torch.h>
 
+#include <cstdlib>
+#include <mutex>
+#include <unordered_map>
+
 #include "host_math.h"
 #include "kernels.h"
 
@@ -23,6 +27,85 @@ inline const uint64_t* u64o(const c10::optional<Tensor>& t) {
 inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
 inline void same_device(const Tensor& a, const Tensor& b) {
   TORCH_CHECK(a.device() == b.device(), "tensors on different devices: ", a.device(), " vs ", b.device());
+}
+
+// ---- fast-path companions, built once per table / key tensor and cached ---------------------
+// The persistent kernels (csrc/he/cuda/he_kernels2.cu) want (w, w') interleaved twiddle tables
+// and keys stored next to their Shoup companions. Callers keep passing the plain tensors; the
+// derived ones are cached here, keyed by the data pointer of the tensor they were derived from
+// (the cache holds a reference, so the pointer cannot be recycled while the entry lives).
+struct TableExt {
+  Tensor src, tw2;
+  int qbits = 64;
+};
+struct KeyExt {
+  Tensor src, ext;
+  uint32_t version = 0;
+};
+
+inline bool fast_path_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("HEFL_HE_V1");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
+
+const TableExt& table_ext(const Tensor& tables, const Tensor& consts) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, TableExt> cache;
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(tables.data_ptr());
+  if (it != cache.end() && it->second.src.sizes() == tables.sizes()) return it->second;
+  if (cache.size() > 256) cache.clear();
+  TableExt e;
+  e.src = tables;
+  const int64_t L = tables.size(0), n = tables.size(2);
+  // [L][4][N] = (w, w', iw, iw') planes  ->  [L][2 dir][N][2]
+  e.tw2 = tables.view({L, 2, 2, n}).permute({0, 1, 3, 2}).contiguous();
+  Tensor q = consts.select(1, 0).cpu();
+  int bits = 0;
+  for (int64_t l = 0; l < L; ++l) {
+    const uint64_t v = (uint64_t)q.data_ptr<int64_t>()[l];
+    bits = std::max(bits, 64 - __builtin_clzll(v));
+  }
+  e.qbits = bits;
+  return cache[tables.data_ptr()] = std::move(e);
+}
+
+// x [..., L, N] (rows cycle through the limbs) -> [..., L, N, 2] = (x, floor(x * 2^64 / q_limb))
+Tensor with_shoup(const Tensor& x, const Tensor& consts, int64_t L) {
+  const int64_t n = x.size(-1);
+  const int64_t rows = x.numel() / n;
+  auto shape = x.sizes().vec();
+  shape.push_back(2);
+  Tensor out = at::empty(shape, x.options());
+  if (x.is_cuda())
+    hefl::cuda::shoup_pairs(u64(x), u64(out), rows, (int)L, (int)n, u64(consts), cur_stream());
+  else
+    hefl::host::shoup_pairs(u64(x), u64(out), rows, (int)L, (int)n, u64(consts));
+  return out;
+}
+
+const Tensor& key_ext(const Tensor& key, const Tensor& consts, int64_t L) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, KeyExt> cache;
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(key.data_ptr());
+  if (it != cache.end() && it->second.version == key._version() && it->second.src.sizes() == key.sizes())
+    return it->second.ext;
+  if (cache.size() > 256) cache.clear();
+  KeyExt e;
+  e.src = key;
+  e.version = key._version();
+  e.ext = with_shoup(key, consts, L);
+  return (cache[key.data_ptr()] = std::move(e)).ext;
+}
+
+Tensor shoup_pairs(const Tensor& x, const Tensor& consts, int64_t L) {
+  same_device(x, consts);
+  TORCH_CHECK(x.is_contiguous(), "expected contiguous tensor");
+  return with_shoup(x, consts, L);
 }
 
 Tensor gen_primes(int64_t bits, int64_t logn, int64_t count, at::IntArrayRef exclude) {
@@ -56,9 +139,14 @@ void ntt_(Tensor data, const Tensor& tables, const Tensor& consts, int64_t L, in
   const int64_t n = 1ll << logn;
   TORCH_CHECK(data.size(-1) == n, "last dim must be N");
   const int64_t rows = data.numel() / n;
-  if (data.is_cuda())
+  if (data.is_cuda()) {
+    if (fast_path_enabled() && tables.size(0) == L && rows % L == 0) {
+      const TableExt& te = table_ext(tables, consts);
+      if (hefl::cuda::ntt2(u64(data), rows, (int)L, (int)logn, u64(te.tw2), u64(consts), te.qbits, inverse, cur_stream()))
+        return;
+    }
     hefl::cuda::ntt(u64(data), rows, (int)L, (int)logn, u64(tables), u64(consts), inverse, cur_stream());
-  else
+  } else
     hefl::host::ntt(u64(data), rows, (int)L, (int)logn, u64(tables), u64(consts), inverse);
 }
 
@@ -219,10 +307,19 @@ void encrypt_out(const c10::optional<Tensor>& msg, const Tensor& pk, int64_t C, 
     TORCH_CHECK(msg->numel() == C * n && msg->is_contiguous(), "msg must be contiguous [C,N]");
     mp = msg->data_ptr<int64_t>();
   }
-  if (pk.is_cuda())
+  if (pk.is_cuda()) {
+    if (fast_path_enabled() && tables.size(0) == L) {
+      const TableExt& te = table_ext(tables, consts);
+      if (hefl::cuda::ntt2_supported((int)logn, (int)L, te.qbits) && logn <= 13) {
+        const Tensor& pkx = key_ext(pk, consts, L);
+        if (hefl::cuda::encrypt2(mp, u64(pkx), u64(ct), C, (int)L, (int)logn, u64(te.tw2), u64(consts),
+                                 u64o(msg_scale), (uint64_t)seed, (uint32_t)ct_offset, te.qbits, cur_stream()))
+          return;
+      }
+    }
     hefl::cuda::encrypt(mp, u64(pk), u64(ct), C, (int)L, (int)logn, u64(tables), u64(consts),
                         u64o(msg_scale), (uint64_t)seed, (uint32_t)ct_offset, cur_stream());
-  else
+  } else
     hefl::host::encrypt(mp, u64(pk), u64(ct), C, (int)L, (int)logn, u64(tables), u64(consts),
                         u64o(msg_scale), (uint64_t)seed, (uint32_t)ct_offset);
 }
@@ -242,9 +339,19 @@ Tensor decrypt(const Tensor& ct, const Tensor& sk, int64_t k, int64_t logn, cons
   const int64_t C = ct.size(0), Lct = ct.size(2), n = ct.size(3);
   TORCH_CHECK(k >= 1 && k <= Lct, "bad k");
   Tensor out = at::empty({C, k, n}, ct.options());
-  if (ct.is_cuda())
+  if (ct.is_cuda()) {
+    if (fast_path_enabled()) {
+      const TableExt& te = table_ext(tables, consts);
+      const int64_t Ltab = tables.size(0);
+      if (hefl::cuda::ntt2_supported((int)logn, (int)k, te.qbits) && sk.numel() == Ltab * n) {
+        const Tensor& skx = key_ext(sk, consts, Ltab);
+        if (hefl::cuda::decrypt2(u64(ct), u64(skx), u64(out), C, (int)Lct, (int)k, (int)logn, u64(te.tw2),
+                                 u64(consts), (int)Ltab, te.qbits, cur_stream()))
+          return out;
+      }
+    }
     hefl::cuda::decrypt(u64(ct), u64(sk), u64(out), C, (int)Lct, (int)k, (int)logn, u64(tables), u64(consts), cur_stream());
-  else
+  } else
     hefl::host::decrypt(u64(ct), u64(sk), u64(out), C, (int)Lct, (int)k, (int)logn, u64(tables), u64(consts));
   return out;
 }
@@ -333,5 +440,6 @@ TORCH_LIBRARY_FRAGMENT(hefl, m) {
   m.def("frac_decode(Tensor coeffs, int int_digits, int frac_digits) -> Tensor", &frac_decode);
   m.def("bfv_scale_round(Tensor x, int q, int p) -> Tensor", &bfv_scale_round);
   m.def("digit_extract(Tensor x, int shift, int bits) -> Tensor", &digit_extract);
+  m.def("shoup_pairs(Tensor x, Tensor consts, int L) -> Tensor", &shoup_pairs);
   m.def("launch_count() -> int", &launch_count);
 }

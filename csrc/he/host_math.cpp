@@ -497,5 +497,17 @@ void digit_extract(const uint64_t* x, int64_t rows, int n, int shift, int bits, 
   for (int64_t g = 0; g < rows * (int64_t)n; ++g) out[g] = (x[g] >> shift) & mask;
 }
 
+void shoup_pairs(const uint64_t* x, uint64_t* out, int64_t rows, int L, int n, const uint64_t* consts) {
+#pragma omp parallel for schedule(static)
+  for (int64_t r = 0; r < rows; ++r) {
+    const uint64_t q = consts[(size_t)(r % L) * kConstStride];
+    for (int i = 0; i < n; ++i) {
+      const uint64_t v = x[r * n + i];
+      out[(r * n + i) * 2] = v;
+      out[(r * n + i) * 2 + 1] = (uint64_t)(((u128)v << 64) / q);
+    }
+  }
+}
+
 }  // namespace host
 }  // namespace hefl

@@ -58,6 +58,8 @@ void frac_decode(const int64_t* coeffs, int64_t C, int n, int int_digits, int fr
                  double* out);
 void bfv_scale_round(const uint64_t* x, int64_t C, int n, uint64_t q, uint64_t p, int64_t* out);
 void digit_extract(const uint64_t* x, int64_t rows, int n, int shift, int bits, uint64_t* out);
+// rows [rows][n] (row r belongs to limb r % L) -> [rows][n][2] = (x, floor(x * 2^64 / q))
+void shoup_pairs(const uint64_t* x, uint64_t* out, int64_t rows, int L, int n, const uint64_t* consts);
 
 }  // namespace host
 }  // namespace hefl

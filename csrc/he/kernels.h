@@ -46,6 +46,23 @@ void bfv_scale_round(const uint64_t* x, int64_t C, int n, uint64_t q, uint64_t p
 void digit_extract(const uint64_t* x, int64_t rows, int n, int shift, int bits, uint64_t* out,
                    cudaStream_t st);
 
+// ---- second-generation persistent kernels (csrc/he/cuda/he_kernels2.cu) ----
+// tw2: [L][2][N][2] interleaved (w, w') tables (forward, inverse); pkx: [2][L][N][2] (pk, pk');
+// skx: [L][N][2] (s, s'); qbits: bit length of the largest prime. Each returns false (and
+// launches nothing) when the parameters are outside the fast path: the caller falls back.
+bool ntt2_supported(int logn, int L, int qbits);
+bool ntt2(uint64_t* data, int64_t rows, int L, int logn, const uint64_t* tw2, const uint64_t* consts, int qbits,
+          bool inverse, cudaStream_t st);
+bool encrypt2(const int64_t* msg, const uint64_t* pkx, uint64_t* ct, int64_t C, int L, int logn, const uint64_t* tw2,
+              const uint64_t* consts, const uint64_t* msg_scale, uint64_t seed, uint32_t ct_offset, int qbits,
+              cudaStream_t st);
+bool decrypt2(const uint64_t* ct, const uint64_t* skx, uint64_t* out, int64_t C, int Lct, int k, int logn,
+              const uint64_t* tw2, const uint64_t* consts, int Ltab, int qbits, cudaStream_t st);
+
+// rows [rows][n] (row r belongs to limb r % L) -> [rows][n][2] = (x, floor(x * 2^64 / q))
+void shoup_pairs(const uint64_t* x, uint64_t* out, int64_t rows, int L, int n, const uint64_t* consts,
+                 cudaStream_t st);
+
 // Number of kernels launched by this library since process start (bench.py's gpu_launches).
 uint64_t launch_count();
 void note_launch(uint64_t n = 1);

@@ -53,8 +53,8 @@ HEFL_HD int popc32(uint32_t v) {
 
 // Streams (c3 of the counter).
 enum : uint32_t {
-  STREAM_ENC_A = 0,   // u, e0
-  STREAM_ENC_B = 1,   // e1
+  STREAM_ENC_A = 0,   // u, e0, e1 (one call per coefficient)
+  STREAM_ENC_B = 1,   // (unused since the single-call sampler; kept so stream numbers stay stable)
   STREAM_SK = 2,      // secret key
   STREAM_PK_E = 3,    // public-key error
   STREAM_UNIFORM = 4  // uniform mod q (c2 carries the limb)
@@ -72,16 +72,21 @@ struct EncNoise {
   int u, e0, e1;
 };
 
-// Encryption randomness for coefficient i of ciphertext ct.
-HEFL_HD EncNoise sample_enc_noise(uint64_t seed, uint32_t ct, uint32_t i) {
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-  Philox4 a = philox4x32_10(i, ct, 0u, STREAM_ENC_A, k0, k1);
-  Philox4 b = philox4x32_10(i, ct, 0u, STREAM_ENC_B, k0, k1);
+// All encryption randomness of one coefficient from ONE Philox call (128 bits): u from word x,
+// e0 from the low 21 bits of y and z, e1 from the low 21 bits of w against the 21 bits made of
+// w[21..31] and y[21..31] -- 32 + 42 + 42 disjoint bits. Philox is 65 instructions per call; with
+// one call the sampler costs ~1/7 of the three NTTs it feeds instead of ~1/2.
+HEFL_HD EncNoise enc_noise_from(const Philox4& a) {
   EncNoise n;
   n.u = ternary_from(a.x);
   n.e0 = cbd21_from(a.y, a.z);
-  n.e1 = cbd21_from(b.x, b.y);
+  n.e1 = cbd21_from(a.w, (a.w >> 21) | ((a.y >> 21) << 11));
   return n;
+}
+
+// Encryption randomness for coefficient i of ciphertext ct.
+HEFL_HD EncNoise sample_enc_noise(uint64_t seed, uint32_t ct, uint32_t i) {
+  return enc_noise_from(philox4x32_10(i, ct, 0u, STREAM_ENC_A, (uint32_t)seed, (uint32_t)(seed >> 32)));
 }
 
 HEFL_HD int sample_ternary(uint64_t seed, uint32_t stream, uint32_t i) {

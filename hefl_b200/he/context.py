@@ -93,6 +93,7 @@ class CKKSContext:
         self.consts_cpu = consts
         self.q0_inv_q1 = pow(self.primes[0], -1, self.primes[1]) if self.L > 1 else 0
         self.device = torch.device("cpu")
+        self._limb_cache = {}
         self.tables, self.consts, self.rot, self.ksi = tables, consts, rot, ksi
         self.to(device)
 
@@ -365,7 +366,13 @@ class CKKSContext:
         return r0, r1
 
     def _limb_views(self, limb: int):
-        return (self.tables[limb:limb + 1].contiguous(), self.consts[limb:limb + 1].contiguous())
+        # cached: the native layer keys its derived (interleaved) tables on these tensors
+        key = (limb, str(self.device))
+        v = self._limb_cache.get(key)
+        if v is None:
+            v = (self.tables[limb:limb + 1].contiguous(), self.consts[limb:limb + 1].contiguous())
+            self._limb_cache[key] = v
+        return v
 
     def _ntt_single_limb(self, x: torch.Tensor, limb: int, inverse: bool) -> None:
         t, c = self._limb_views(limb)

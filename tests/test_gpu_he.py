@@ -16,7 +16,8 @@ def _ctx_pair(n, bits, scale_bits=40):
     return c, g
 
 
-@pytest.mark.parametrize("logn,bits", [(10, (27,)), (12, (36, 36, 37)), (13, (54, 54, 54, 55)),
+@pytest.mark.parametrize("logn,bits", [(10, (27,)), (11, (54,)), (12, (36, 36, 37)), (12, (54, 55)), (12, (58, 57)),
+                                       (13, (54, 54, 54, 55)), (13, (40,) * 8), (14, (54, 54, 54, 54)),
                                        (14, (60, 59, 58)), (15, (60, 60))])
 def test_ntt_gpu_matches_cpu(logn, bits):
     n = 1 << logn
@@ -52,8 +53,8 @@ def test_pointwise_and_reduce_gpu_match_cpu():
     assert torch.equal(out.cpu(), ref)
 
 
-@pytest.mark.parametrize("n,bits", [(4096, (36, 36, 37)), (8192, (54, 54, 54, 55)), (16384, (54, 54, 54, 54)),
-                                    (32768, (60, 60))])
+@pytest.mark.parametrize("n,bits", [(1024, (27,)), (2048, (54,)), (4096, (36, 36, 37)), (4096, (58, 50)),
+                                    (8192, (54, 54, 54, 55)), (16384, (54, 54, 54, 54)), (32768, (60, 60))])
 def test_encrypt_decrypt_gpu_bit_exact_vs_cpu(n, bits):
     c, g = _ctx_pair(n, bits)
     sk, pk = c.keygen(seed=5)

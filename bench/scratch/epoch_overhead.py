@@ -1,7 +1,7 @@
 """Where does a round's time go beyond (steps x step time)? Times fit() of the medical CNN for E epochs
 with CUDA events and host timestamps around the epoch boundaries."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from hefl_b200.config import FLConfig
 from hefl_b200.models import ParamPack, create_model

@@ -1,6 +1,6 @@
 """Where does a round's time go outside the CUDA graph? (device time per phase)"""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from hefl_b200.config import FLConfig
 from hefl_b200.fl import FederatedRunner

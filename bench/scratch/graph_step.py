@@ -1,7 +1,7 @@
 """Times the captured training-step CUDA graph of the medical CNN (tcgen05 engine): median of
 N replays on fresh data indices, L2 flushed between replays. HEFL_PDL=0/1 toggles PDL."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from hefl_b200.config import FLConfig
 from hefl_b200.models import ParamPack, create_model

@@ -1,6 +1,6 @@
 """Bottleneck isolation for the layer-1/2 forward kernel: skip TMA / MMA / epilogue in turn."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from hefl_b200 import _ext
 ops = _ext.ops()

@@ -1,6 +1,6 @@
 """Runs a few eager training steps of the medical CNN on the tcgen05 engine (for ncu)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from hefl_b200.config import FLConfig
 from hefl_b200.models import ParamPack, create_model

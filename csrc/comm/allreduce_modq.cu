@@ -5,9 +5,10 @@
 //
 // Buffer layout on every rank: [C][2][L][N] u64 residues (< q_l < 2^61), symmetric address
 // space (peer r's buffer is mapped at bufs[r]). Three algorithms:
-//   two_shot  : rank r owns chunk r. It pulls chunk r from all P peers with 16-byte loads,
-//               adds, reduces mod q_l in registers and pushes the result into chunk r of all
-//               P buffers (in place).
+//   two_shot  : rank r owns chunk r. It pulls chunk r from all P peers with 32-byte loads
+//               (ld.global.v4.u64, two per peer in flight), adds, reduces mod q_l in registers
+//               and pushes the result into chunk r of all P buffers (in place). With a key
+//               holder, that rank owns no chunk: it never reads un-aggregated ciphertext.
 //   one_shot  : every rank pulls everything and writes a private output (latency-optimal for
 //               small messages).
 //   multimem  : as two_shot but the P-way add is done by the NVSwitch
@@ -21,6 +22,7 @@
 
 #include "../he/kernels.h"
 #include "../he/modarith.h"
+#include "../he/philox.h"
 #include "comm.h"
 
 namespace hefl {
@@ -81,13 +83,28 @@ __device__ __forceinline__ bool block_barrier(const AllReduceArgs& a, int slot, 
   return ok_flag != 0;
 }
 
-__device__ __forceinline__ ulonglong2 ld16(const uint64_t* p) {
-  ulonglong2 v;
-  asm volatile("ld.global.relaxed.sys.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+// 32-byte peer accesses (sm_100: ld/st.global.v4.u64). Relaxed at system scope: ordering
+// against the other GPUs comes from the release/acquire flag barriers around the data phase.
+struct U64x4 {
+  uint64_t v[4];
+};
+__device__ __forceinline__ U64x4 ld32(const uint64_t* p) {
+  U64x4 r;
+  asm volatile("ld.global.relaxed.sys.v4.u64 {%0, %1, %2, %3}, [%4];"
+               : "=l"(r.v[0]), "=l"(r.v[1]), "=l"(r.v[2]), "=l"(r.v[3]) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void st32(uint64_t* p, const U64x4& r) {
+  asm volatile("st.global.relaxed.sys.v4.u64 [%0], {%1, %2, %3, %4};"
+               :: "l"(p), "l"(r.v[0]), "l"(r.v[1]), "l"(r.v[2]), "l"(r.v[3]) : "memory");
+}
+__device__ __forceinline__ uint64_t mm_ld_add(const uint64_t* mc) {
+  uint64_t v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u64 %0, [%1];" : "=l"(v) : "l"(mc) : "memory");
   return v;
 }
-__device__ __forceinline__ void st16(uint64_t* p, ulonglong2 v) {
-  asm volatile("st.global.relaxed.sys.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(v.x), "l"(v.y) : "memory");
+__device__ __forceinline__ void mm_st(uint64_t* mc, uint64_t v) {
+  asm volatile("multimem.st.relaxed.sys.global.u64 [%0], %1;" :: "l"(mc), "l"(v) : "memory");
 }
 
 __device__ __forceinline__ uint64_t mod_sum(uint64_t s, uint64_t q, uint64_t ratio_hi) {
@@ -98,6 +115,11 @@ __device__ __forceinline__ uint64_t mod_sum(uint64_t s, uint64_t q, uint64_t rat
   return r;
 }
 
+// Work is cut into "quads" of 4 words (32 bytes). A quad never straddles a limb (N >= 1024),
+// so q is fetched once per quad.
+constexpr int kUnroll = 1;      // quads per thread per step in the P2P algorithms: P * 32 B in flight per thread (2 spill)
+constexpr int kMmUnroll = 2;    // quads per thread per step for multimem: 8 independent ld_reduce in flight
+
 template <int ALGO>  // 0 two_shot, 1 one_shot, 2 multimem
 __global__ void __launch_bounds__(512)
 allreduce_modq_kernel(const __grid_constant__ AllReduceArgs a) {
@@ -105,50 +127,92 @@ allreduce_modq_kernel(const __grid_constant__ AllReduceArgs a) {
   if (!block_barrier(a, 0, deadline)) return;
 
   const int P = a.world;
-  const int64_t pairs = a.numel >> 1;  // 16-byte units
-  int64_t lo = 0, hi = pairs;
-  if (ALGO != 1) {  // chunk ownership, aligned to 16 bytes
-    const int64_t per = (pairs + P - 1) / P;
-    lo = per * a.rank;
-    hi = lo + per < pairs ? lo + per : pairs;
-    if (lo > pairs) lo = pairs;
+  const int64_t quads = a.numel >> 2;
+  int64_t lo = 0, hi = quads;
+  if (ALGO != 1) {
+    // Chunk ownership. With a key holder (a.no_owner >= 0) that rank owns nothing: it never
+    // loads a peer's un-aggregated ciphertext, it only receives finished sums.
+    const int owners = a.no_owner >= 0 ? P - 1 : P;
+    const int me = a.no_owner >= 0 ? (a.rank == a.no_owner ? -1 : a.rank - (a.rank > a.no_owner ? 1 : 0)) : a.rank;
+    if (me < 0) {
+      lo = hi = 0;
+    } else {
+      const int64_t per = (quads + owners - 1) / owners;
+      lo = per * me;
+      hi = lo + per < quads ? lo + per : quads;
+      if (lo > quads) lo = quads;
+    }
   }
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   const int logn = a.logn;
+  uint32_t peer_loads = 0;
 
-  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
-    const int64_t e = i << 1;
-    const int l = (int)((e >> logn) % a.L);
-    const uint64_t q = a.q[l], rh = a.ratio_hi[l];
-    ulonglong2 acc;
-    if (ALGO == 2) {
-      const uint64_t* mc = a.mc + e;
-      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u64 %0, [%1];" : "=l"(acc.x) : "l"(mc) : "memory");
-      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u64 %0, [%1];" : "=l"(acc.y) : "l"(mc + 1) : "memory");
-    } else {
-      ulonglong2 v[kMaxWorld];
+  if (ALGO == 2) {
+    for (int64_t i0 = lo + tid; i0 < hi; i0 += nthreads * kMmUnroll) {
+      uint64_t acc[kMmUnroll][4];
 #pragma unroll
-      for (int p = 0; p < kMaxWorld; ++p)
-        if (p < P) v[p] = ld16(a.bufs[(a.rank + p) % P] + e);  // stagger peers across ranks
-      acc = v[0];
+      for (int u = 0; u < kMmUnroll; ++u) {
+        const int64_t i = i0 + u * nthreads;
+        if (i < hi) {
+          const uint64_t* mc = a.mc + (i << 2);
 #pragma unroll
-      for (int p = 1; p < kMaxWorld; ++p)
-        if (p < P) { acc.x += v[p].x; acc.y += v[p].y; }
+          for (int k = 0; k < 4; ++k) acc[u][k] = mm_ld_add(mc + k);
+          ++peer_loads;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kMmUnroll; ++u) {
+        const int64_t i = i0 + u * nthreads;
+        if (i < hi) {
+          const int l = (int)(((i << 2) >> logn) % a.L);
+          const uint64_t q = a.q[l], rh = a.ratio_hi[l];
+          uint64_t* mc = a.mc + (i << 2);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mm_st(mc + k, mod_sum(acc[u][k], q, rh));
+        }
+      }
     }
-    acc.x = mod_sum(acc.x, q, rh);
-    acc.y = mod_sum(acc.y, q, rh);
-    if (ALGO == 1) {
-      *reinterpret_cast<ulonglong2*>(a.out + e) = acc;
-    } else if (ALGO == 2) {
-      uint64_t* mc = a.mc + e;
-      asm volatile("multimem.st.relaxed.sys.global.u64 [%0], %1;" :: "l"(mc), "l"(acc.x) : "memory");
-      asm volatile("multimem.st.relaxed.sys.global.u64 [%0], %1;" :: "l"(mc + 1), "l"(acc.y) : "memory");
-    } else {
+  } else {
+    for (int64_t i0 = lo + tid; i0 < hi; i0 += nthreads * kUnroll) {
+      U64x4 v[kUnroll][kMaxWorld];
 #pragma unroll
-      for (int p = 0; p < kMaxWorld; ++p)
-        if (p < P) st16(a.bufs[(a.rank + p) % P] + e, acc);
+      for (int u = 0; u < kUnroll; ++u) {
+        const int64_t i = i0 + u * nthreads;
+        if (i < hi) {
+#pragma unroll
+          for (int p = 0; p < kMaxWorld; ++p)
+            if (p < P) v[u][p] = ld32(a.bufs[(a.rank + p) % P] + (i << 2));  // stagger peers across ranks
+          ++peer_loads;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int64_t i = i0 + u * nthreads;
+        if (i < hi) {
+          const int l = (int)(((i << 2) >> logn) % a.L);
+          const uint64_t q = a.q[l], rh = a.ratio_hi[l];
+          U64x4 acc = v[u][0];
+#pragma unroll
+          for (int p = 1; p < kMaxWorld; ++p)
+            if (p < P) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) acc.v[k] += v[u][p].v[k];
+            }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc.v[k] = mod_sum(acc.v[k], q, rh);
+          if (ALGO == 1) {
+            st32(a.out + (i << 2), acc);
+          } else {
+#pragma unroll
+            for (int p = 0; p < kMaxWorld; ++p)
+              if (p < P) st32(a.bufs[(a.rank + p) % P] + (i << 2), acc);
+          }
+        }
+      }
     }
   }
+  if (a.stats && peer_loads) atomicAdd(a.stats, peer_loads);
   // make this block's peer stores visible before signalling completion
   __threadfence_system();
   block_barrier(a, 1, deadline);
@@ -160,6 +224,44 @@ void allreduce_modq(const AllReduceArgs& args, int algo, int blocks, int threads
     case 1: allreduce_modq_kernel<1><<<blocks, threads, 0, st>>>(args); break;
     default: allreduce_modq_kernel<2><<<blocks, threads, 0, st>>>(args); break;
   }
+  hefl::cuda::note_launch();
+}
+
+// Pairwise additive masks (secure-aggregation style): for every peer j the word w of this rank's
+// ciphertext gets +PRG(seed_ij, w) if sign_j > 0 and -PRG(seed_ij, w) if sign_j < 0, modulo the
+// limb prime. Rank i uses sign(+) for j > i and (-) for j < i with the SAME pair seed, so the masks
+// cancel in the sum over ranks while every individual buffer is uniformly random to anybody who
+// does not hold all of that rank's pair seeds. One Philox call yields the masks of two words.
+__global__ void __launch_bounds__(256)
+pairwise_mask_kernel(uint64_t* __restrict__ data, int64_t numel, int L, int logn, MaskArgs m) {
+  const int64_t pairs = numel >> 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i << 1;
+    const int l = (int)((e >> logn) % L);
+    const Modulus mod{m.q[l], m.ratio_lo[l], m.ratio_hi[l]};
+    ulonglong2 v = *reinterpret_cast<ulonglong2*>(data + e);
+    for (int j = 0; j < m.npeers; ++j) {
+      const Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), m.round, 9u, (uint32_t)m.seed[j],
+                                      (uint32_t)(m.seed[j] >> 32));
+      const uint64_t a0 = barrett_reduce_64(((uint64_t)r.x << 32) | r.y, mod);
+      const uint64_t a1 = barrett_reduce_64(((uint64_t)r.z << 32) | r.w, mod);
+      if (m.sign[j] > 0) {
+        v.x = add_mod(v.x, a0, mod.q);
+        v.y = add_mod(v.y, a1, mod.q);
+      } else {
+        v.x = sub_mod(v.x, a0, mod.q);
+        v.y = sub_mod(v.y, a1, mod.q);
+      }
+    }
+    *reinterpret_cast<ulonglong2*>(data + e) = v;
+  }
+}
+
+void pairwise_mask(uint64_t* data, int64_t numel, int L, int logn, const MaskArgs& m, cudaStream_t st) {
+  if (numel == 0 || m.npeers == 0) return;
+  int blocks = (int)(((numel >> 1) + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  pairwise_mask_kernel<<<blocks, 256, 0, st>>>(data, numel, L, logn, m);
   hefl::cuda::note_launch();
 }
 

@@ -17,10 +17,22 @@ struct AllReduceArgs {
   uint32_t* status;            // local diagnostic word (0 = ok)
   uint64_t q[kMaxLimbs];
   uint64_t ratio_hi[kMaxLimbs];  // floor(2^64 / q)
-  int64_t numel;               // u64 words, even
+  int64_t numel;               // u64 words, multiple of 4
   uint64_t timeout_ns;
   int rank, world, L, logn;
+  int no_owner;                // rank that owns no chunk (the secret-key holder) or -1
+  uint32_t* stats;             // optional: += number of 32-byte peer-load steps issued by this rank
 };
+
+struct MaskArgs {
+  uint64_t seed[kMaxWorld];    // pair seed shared with peer j
+  int sign[kMaxWorld];         // +1 / -1
+  int npeers;
+  uint32_t round;
+  uint64_t q[kMaxLimbs], ratio_lo[kMaxLimbs], ratio_hi[kMaxLimbs];
+};
+void pairwise_mask(uint64_t* data, int64_t numel, int L, int logn, const MaskArgs& m, cudaStream_t st);
+void pairwise_mask_host(uint64_t* data, int64_t numel, int L, int logn, const MaskArgs& m);
 
 // algo: 0 two_shot, 1 one_shot, 2 multimem. Needs 2 * blocks * world u32 flags per pad.
 void allreduce_modq(const AllReduceArgs& args, int algo, int blocks, int threads, cudaStream_t st);

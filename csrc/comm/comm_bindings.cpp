@@ -9,7 +9,39 @@
 #include <cstring>
 
 #include "../he/modarith.h"
+#include "../he/philox.h"
 #include "comm.h"
+
+namespace hefl {
+namespace comm {
+// CPU twin of pairwise_mask_kernel (gloo / loopback transports, tests).
+void pairwise_mask_host(uint64_t* data, int64_t numel, int L, int logn, const MaskArgs& m) {
+  const int64_t pairs = numel >> 1;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < pairs; ++i) {
+    const int64_t e = i << 1;
+    const int l = (int)((e >> logn) % L);
+    const Modulus mod{m.q[l], m.ratio_lo[l], m.ratio_hi[l]};
+    uint64_t x = data[e], y = data[e + 1];
+    for (int j = 0; j < m.npeers; ++j) {
+      const Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), m.round, 9u, (uint32_t)m.seed[j],
+                                      (uint32_t)(m.seed[j] >> 32));
+      const uint64_t a0 = barrett_reduce_64(((uint64_t)r.x << 32) | r.y, mod);
+      const uint64_t a1 = barrett_reduce_64(((uint64_t)r.z << 32) | r.w, mod);
+      if (m.sign[j] > 0) {
+        x = add_mod(x, a0, mod.q);
+        y = add_mod(y, a1, mod.q);
+      } else {
+        x = sub_mod(x, a0, mod.q);
+        y = sub_mod(y, a1, mod.q);
+      }
+    }
+    data[e] = x;
+    data[e + 1] = y;
+  }
+}
+}  // namespace comm
+}  // namespace hefl
 
 namespace {
 
@@ -23,11 +55,14 @@ inline uint64_t* u64(const Tensor& t) {
 void allreduce_modq(at::IntArrayRef buf_ptrs, at::IntArrayRef sig_ptrs, int64_t mc_ptr,
                     const c10::optional<Tensor>& out, const Tensor& status, const Tensor& consts_cpu,
                     int64_t numel, int64_t L, int64_t logn, int64_t rank, int64_t world, int64_t algo,
-                    int64_t blocks, int64_t threads, int64_t timeout_ms) {
+                    int64_t blocks, int64_t threads, int64_t timeout_ms, int64_t no_owner,
+                    const c10::optional<Tensor>& stats) {
   TORCH_CHECK(world >= 1 && world <= hefl::comm::kMaxWorld, "world size must be 1..8");
   TORCH_CHECK((int64_t)buf_ptrs.size() == world && (int64_t)sig_ptrs.size() == world, "need one pointer per rank");
   TORCH_CHECK(L >= 1 && L <= hefl::comm::kMaxLimbs, "too many limbs");
-  TORCH_CHECK(numel % 2 == 0, "numel must be even");
+  TORCH_CHECK(numel % 4 == 0, "numel must be a multiple of 4 words");
+  TORCH_CHECK(no_owner < world, "no_owner must be a rank or -1");
+  TORCH_CHECK(!(no_owner >= 0 && (algo == 1 || world < 2)), "a key holder needs two_shot / multimem and >= 2 ranks");
   TORCH_CHECK(consts_cpu.is_cpu() && consts_cpu.size(0) >= L, "consts_cpu must be the CPU consts table");
   TORCH_CHECK(threads >= world && threads <= 512 && threads % 32 == 0, "bad thread count");
   hefl::comm::AllReduceArgs a;
@@ -55,8 +90,40 @@ void allreduce_modq(at::IntArrayRef buf_ptrs, at::IntArrayRef sig_ptrs, int64_t 
   a.world = (int)world;
   a.L = (int)L;
   a.logn = (int)logn;
+  a.no_owner = (int)no_owner;
+  if (stats.has_value()) {
+    TORCH_CHECK(stats->is_cuda() && stats->scalar_type() == at::kInt, "stats must be a CUDA int32 tensor");
+    a.stats = reinterpret_cast<uint32_t*>(stats->data_ptr<int32_t>());
+  }
   hefl::comm::allreduce_modq(a, (int)algo, (int)blocks, (int)threads,
                              at::cuda::getCurrentCUDAStream().stream());
+}
+
+// data (+)= sum_j sign_j * PRG(seed_j) mod q, in place (pairwise masks that cancel in the all-reduce).
+void pairwise_mask_(Tensor data, at::IntArrayRef seeds, at::IntArrayRef signs, int64_t round, int64_t L,
+                    int64_t logn, const Tensor& consts_cpu) {
+  TORCH_CHECK(seeds.size() == signs.size() && seeds.size() <= (size_t)hefl::comm::kMaxWorld, "bad peer list");
+  TORCH_CHECK(data.numel() % 2 == 0, "numel must be even");
+  TORCH_CHECK(consts_cpu.is_cpu() && consts_cpu.size(0) >= L && L <= hefl::comm::kMaxLimbs, "bad consts");
+  hefl::comm::MaskArgs m;
+  std::memset(&m, 0, sizeof(m));
+  m.npeers = (int)seeds.size();
+  for (int j = 0; j < m.npeers; ++j) {
+    m.seed[j] = (uint64_t)seeds[j];
+    m.sign[j] = signs[j] >= 0 ? 1 : -1;
+  }
+  m.round = (uint32_t)round;
+  const uint64_t* cc = reinterpret_cast<const uint64_t*>(consts_cpu.data_ptr<int64_t>());
+  for (int l = 0; l < L; ++l) {
+    m.q[l] = cc[l * 8];
+    m.ratio_lo[l] = cc[l * 8 + 1];
+    m.ratio_hi[l] = cc[l * 8 + 2];
+  }
+  if (data.is_cuda()) {
+    hefl::comm::pairwise_mask(u64(data), data.numel(), (int)L, (int)logn, m, at::cuda::getCurrentCUDAStream().stream());
+  } else {
+    hefl::comm::pairwise_mask_host(u64(data), data.numel(), (int)L, (int)logn, m);
+  }
 }
 
 void local_sum_modq(at::TensorList srcs, Tensor out, int64_t L, int64_t logn, const Tensor& consts) {
@@ -144,7 +211,8 @@ Tensor tensor_from_ptr(int64_t ptr, int64_t numel, int64_t device) {
 }  // namespace
 
 TORCH_LIBRARY_FRAGMENT(hefl, m) {
-  m.def("allreduce_modq(int[] buf_ptrs, int[] sig_ptrs, int mc_ptr, Tensor? out, Tensor status, Tensor consts_cpu, int numel, int L, int logn, int rank, int world, int algo, int blocks, int threads, int timeout_ms) -> ()", &allreduce_modq);
+  m.def("allreduce_modq(int[] buf_ptrs, int[] sig_ptrs, int mc_ptr, Tensor? out, Tensor status, Tensor consts_cpu, int numel, int L, int logn, int rank, int world, int algo, int blocks, int threads, int timeout_ms, int no_owner=-1, Tensor? stats=None) -> ()", &allreduce_modq);
+  m.def("pairwise_mask_(Tensor(a!) data, int[] seeds, int[] signs, int round, int L, int logn, Tensor consts_cpu) -> ()", &pairwise_mask_);
   m.def("local_sum_modq(Tensor[] srcs, Tensor(a!) out, int L, int logn, Tensor consts) -> ()", &local_sum_modq);
   m.def("ipc_alloc(int nbytes, int device) -> Tensor", &ipc_alloc);
   m.def("ipc_get_handle(Tensor t) -> Tensor", &ipc_get_handle);

@@ -113,7 +113,9 @@ struct TapGemmArgs {
   int num_tiles;
   int P;                // B*H*W
   int co_total;         // output channels of the layer (CO per CTA column block = blockIdx.y)
-  int dbg;              // bottleneck isolation (bench only): 1 = skip TMA data, 2 = skip MMAs, 4 = skip epilogue work
+#ifdef HEFL_CONV_DEBUG
+  int dbg;              // bottleneck isolation, ONLY in -DHEFL_CONV_DEBUG builds: 1 = skip TMA data, 2 = skip MMAs, 4 = skip epilogue
+#endif
   const float* bias;    // [CO] (POOL)
   __nv_bfloat16* out;   // POOL: [B,Hp,Wp,CO]; else [P,CO]
   uint8_t* argmax;      // POOL, may be null
@@ -240,9 +242,12 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           seg_stride = -a.W;                     // segment r starts at m0 - r*W - 2
         }
         mbar_wait(&empty[buf], phase ^ 1);
+#ifdef HEFL_CONV_DEBUG
         if (a.dbg & 1) {
           mbar_arrive(&full[buf]);
-        } else {
+        } else
+#endif
+        {
           mbar_expect_tx(&full[buf], Cfg::HALO);
           uint8_t* dst = sA + buf * Cfg::HALO;
           for (int kb = 0; kb < Cfg::NKB; ++kb)
@@ -276,7 +281,10 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         constexpr uint32_t hi = desc_hi(8 * Cfg::ROW_BYTES, Cfg::ROW_BYTES);
 #pragma unroll
         for (int j = 0; j < Cfg::NACC; ++j) {
-          if (j != jme || (a.dbg & 2)) continue;
+#ifdef HEFL_CONV_DEBUG
+          if (a.dbg & 2) continue;
+#endif
+          if (j != jme) continue;
           const uint32_t d_tmem = tmem_base + (tb * Cfg::NACC + j) * CO;
 #pragma unroll
           for (int tap = 0; tap < Cfg::NTAP; ++tap) {
@@ -323,7 +331,12 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const bool writer = wp < a.Wp;
         const bool odd = (lane & 1) != 0;
 #pragma unroll 1
-        for (int ch = grp; ch < ((a.dbg & 4) ? 0 : CO / 8); ch += 2) {
+#ifdef HEFL_CONV_DEBUG
+        const int ch_end = (a.dbg & 4) ? 0 : CO / 8;
+#else
+        constexpr int ch_end = CO / 8;
+#endif
+        for (int ch = grp; ch < ch_end; ch += 2) {
           float v0[8], v1[8];
           tmem_ld8_nowait(tmem_base + lane_base + (tb * 2 + 0) * CO + ch * 8, v0);
           tmem_ld8_nowait(tmem_base + lane_base + (tb * 2 + 1) * CO + ch * 8, v1);
@@ -436,13 +449,23 @@ static void launch_tap_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Wt, Tap
   hefl::cuda::note_launch();
 }
 
+// The work-skipping switch exists only in -DHEFL_CONV_DEBUG builds (HEFL_NVCC_EXTRA); release kernels carry
+// no such code and conv_set_debug refuses to arm it.
+#ifdef HEFL_CONV_DEBUG
 static int g_dbg = 0;
 void conv_set_debug(int mask) { g_dbg = mask; }
+#else
+void conv_set_debug(int mask) {
+  if (mask != 0) throw std::runtime_error("conv_set_debug: this build has no debug switch (rebuild with -DHEFL_CONV_DEBUG)");
+}
+#endif
 
 void conv_fwd_pool(const void* X, const void* Wf, const float* bias, void* out, uint8_t* argmax, int B, int H,
                    int W, int CK, int CO, int spack, cudaStream_t st) {
   TapGemmArgs a{};
+#ifdef HEFL_CONV_DEBUG
   a.dbg = g_dbg;
+#endif
   a.B = B; a.H = H; a.W = W;
   a.Hp = (H - 2) / 2; a.Wp = (W - 2) / 2;
   a.tiles_w = (2 * a.Wp + 127) / 128;

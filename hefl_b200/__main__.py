@@ -37,6 +37,8 @@ def main(argv=None) -> int:
     extra.add_argument("--checkpoint", default=None)
     extra.add_argument("--data-dir", default=None)
     extra.add_argument("--test-dir", default=None)
+    extra.add_argument("--stream-decode", action="store_true",
+                       help="decode images per batch (flow_from_dataframe semantics) instead of the whole shard up front")
     extra.add_argument("--simulate", action="store_true")
     extra.add_argument("-h", "--help", action="store_true")
     ns, rest = extra.parse_known_args(argv)
@@ -75,7 +77,7 @@ def main(argv=None) -> int:
         from .fl.data import ImageFolderDataset
 
         dataset = ImageFolderDataset(ns.data_dir, cfg.image_size, cfg.in_channels, index=rank, num_clients=world,
-                                     shuffle_seed=cfg.seed)
+                                     shuffle_seed=cfg.seed, stream=ns.stream_decode)
         cfg.num_classes = max(cfg.num_classes, dataset.classes)
     run = FederatedRunner(cfg, rank=rank, world=world, device=device, dataset=dataset)
     if ns.checkpoint and os.path.exists(ns.checkpoint):
@@ -89,8 +91,8 @@ def main(argv=None) -> int:
         if rank == 0:
             print(json.dumps({"round": rec["round"], "loss": rec["loss"], "accuracy": rec["accuracy"],
                               "stage_ms_max": rec["stage_ms_max"], "clients": world, "transport": rec["transport"]}))
-            if ns.checkpoint:
-                run.save_checkpoint(ns.checkpoint)
+        if ns.checkpoint:
+            run.save_checkpoint(ns.checkpoint)       # rank 0: global model; every rank: its own optimiser / RNG state
         if world > 1:
             dist.barrier()
     if ns.test_dir and rank == 0:

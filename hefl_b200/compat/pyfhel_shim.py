@@ -21,6 +21,8 @@ from __future__ import annotations
 import struct
 from typing import Optional, Sequence, Union
 
+import secrets
+
 import numpy as np
 import torch
 
@@ -139,8 +141,11 @@ class Pyfhel:
         self._pk = None
         self._sk = None
         self._rlk = None
+        # Encryption randomness: a fresh OS-entropy seed per instance (a rehydrated get_pk() object is a new
+        # instance, so two clients never draw the same (u, e0, e1)); never derived from the key seed or a
+        # constant -- with predictable randomness anybody holding pk recovers m = c0 - pk0*u - e0.
         self._seed_counter = 0
-        self._enc_seed = 0x5EED
+        self._enc_seed = secrets.randbits(63)
 
     # ------------------------------------------------------------------ context / keys
     def contextGen(self, p: int = 65537, m: int = 2048, flagBatching: bool = False, base: int = 2,
@@ -164,11 +169,17 @@ class Pyfhel:
         self._pk = self._sk = self._rlk = None
 
     def keyGen(self, seed: Optional[int] = None) -> None:
+        """Key pair from OS entropy (the reference seeds nothing, Q12). ``seed`` exists for reproducible tests
+        only; it does not touch the encryption randomness (see ``seed_encryption``)."""
         self._need_ctx()
         if seed is None:
-            seed = int.from_bytes(np.random.bytes(7), "little")    # the reference seeds nothing (Q12)
+            seed = secrets.randbits(63)
         self._sk, self._pk = self._ctx.keygen(seed=seed)
-        self._enc_seed = (seed * 6364136223846793005 + 1442695040888963407) & 0x7FFFFFFFFFFFFFFF
+
+    def seed_encryption(self, seed: int) -> None:
+        """TESTS ONLY: make the following encryptions reproducible."""
+        self._enc_seed = int(seed) & 0x7FFFFFFFFFFFFFFF
+        self._seed_counter = 0
 
     def relinKeyGen(self, bitCount: int = 16, size: int = 1) -> None:
         """SEAL-2.x signature (decomposition bit count, key size); FLPyfhelin.py:362-363."""

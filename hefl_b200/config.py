@@ -54,8 +54,16 @@ class FLConfig:
     clients: int = 2
     rounds: int = 1
     compat_sequential_clients: bool = False   # reproduce quirk Q1 (FLPyfhelin.py:180-193)
-    key_holder: int = -1                      # -1: every client holds the secret key (the reference's notebook owns
-                                              # privatekey.pickle); r >= 0: only rank r decrypts and broadcasts the average
+    key_holder: int = 0                       # rank that GENERATES the key pair (OS entropy), is the only one to keep the
+                                              # secret key, owns no chunk of the fused all-reduce (never loads a peer's
+                                              # un-aggregated ciphertext), decrypts the aggregate and broadcasts the averaged
+                                              # model -- the reference's roles: aggregation with get_pk (FLPyfhelin.py:370),
+                                              # get_sk only in decrypt (:284). -1: rank 0 generates and hands sk to every
+                                              # rank (every client can decrypt; weaker, kept for experiments)
+    deterministic_crypto: bool = False        # tests / debugging ONLY: derive the key pair and every encryption seed from
+                                              # ``seed`` (public!) instead of OS entropy, so runs are bit-reproducible
+    pairwise_masks: bool = False              # add PRG masks (X25519-agreed pair seeds, +/- per pair) to each client's
+                                              # ciphertext before the all-reduce; they cancel in the sum
     allow_dropouts: bool = False              # clients may sit a round out (participation mask): K becomes a runtime
                                               # value agreed by a 1-element all-reduce and folded into the decode scale
     debug_precision: bool = False             # also all-reduce the PLAINTEXT updates and record the CKKS error of the

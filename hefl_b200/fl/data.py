@@ -81,7 +81,8 @@ class ImageFolderDataset:
     label names of the WHOLE folder, so every client agrees on them."""
 
     def __init__(self, folder: str, image_size: int = 256, channels: int = 3, index: int = 0, num_clients: int = 1,
-                 shuffle_seed: Optional[int] = 0, workers: int = 8, pin: Optional[bool] = None):
+                 shuffle_seed: Optional[int] = 0, workers: int = 8, pin: Optional[bool] = None,
+                 stream: bool = False):
         from concurrent.futures import ThreadPoolExecutor
 
         df = prep_df(folder, shuffle=shuffle_seed is not None, seed=shuffle_seed)
@@ -93,6 +94,20 @@ class ImageFolderDataset:
         rows = df.iloc[lo:hi]
         self.filenames = list(rows["Path"])
         n = len(self.filenames)
+        self.image_size, self.channels = image_size, channels
+        labels = torch.tensor([self.class_indices[l] for l in rows["Label"]], dtype=torch.int64)
+        pin = torch.cuda.is_available() if pin is None else pin
+        self.n = n
+        self.classes = len(names)
+        self.stream = bool(stream)
+        if self.stream:
+            # flow_from_dataframe semantics (FLPyfhelin.py:88-112): nothing is decoded up front, every batch is
+            # decoded when it is asked for (``load_batch``), so the shard need not fit in host memory
+            self._pool = ThreadPoolExecutor(max_workers=max(1, workers))
+            self.images = None
+            self.image_shape = (image_size, image_size, channels)
+            self.labels = labels.pin_memory() if pin else labels
+            return
         imgs = torch.zeros(n, image_size, image_size, channels, dtype=torch.uint8)
 
         def load(i: int) -> None:
@@ -100,12 +115,23 @@ class ImageFolderDataset:
 
         with ThreadPoolExecutor(max_workers=max(1, workers)) as ex:
             list(ex.map(load, range(n)))
-        labels = torch.tensor([self.class_indices[l] for l in rows["Label"]], dtype=torch.int64)
-        pin = torch.cuda.is_available() if pin is None else pin
         self.images = imgs.pin_memory() if pin else imgs
+        self.image_shape = tuple(imgs.shape[1:])
         self.labels = labels.pin_memory() if pin else labels
-        self.n = n
-        self.classes = len(names)
+
+    def load_batch(self, sel: torch.Tensor, out: torch.Tensor) -> None:
+        """Decode the images ``sel`` (indices into this shard) into ``out`` [len(sel), H, W, C] uint8 (pinned
+        staging memory of the feeder) on the thread pool."""
+        idx = [int(i) for i in sel]
+
+        def load(k: int) -> None:
+            out[k] = torch.from_numpy(np.ascontiguousarray(_decode(self.filenames[idx[k]], self.image_size, self.channels)))
+
+        if getattr(self, "_pool", None) is not None:
+            list(self._pool.map(load, range(len(idx))))
+        else:
+            for k in range(len(idx)):
+                load(k)
 
     def __len__(self) -> int:
         return self.n
@@ -153,7 +179,12 @@ class BatchFeeder:
         self.copy_stream = torch.cuda.Stream(device) if self.cuda else None
         n = len(self.indices)
         self.steps = n // batch_size if drop_last else (n + batch_size - 1) // batch_size
-        shp = (batch_size, *ds.images.shape[1:])
+        self.streaming = getattr(ds, "images", None) is None      # decode-per-batch dataset (ImageFolderDataset(stream=True))
+        img_shape = tuple(ds.image_shape) if self.streaming else tuple(ds.images.shape[1:])
+        shp = (batch_size, *img_shape)
+        self._stage_x = ([torch.empty(shp, dtype=torch.uint8).pin_memory() if self.cuda else torch.empty(shp, dtype=torch.uint8)
+                          for _ in range(2)] if self.streaming else None)
+        self._pending = [False, False]      # slot has an H2D copy in flight that still reads its pinned staging
         self._stage_y = [torch.empty(batch_size, dtype=torch.int64).pin_memory() if self.cuda
                          else torch.empty(batch_size, dtype=torch.int64) for _ in range(2)]
         self._dev_x = [torch.empty(shp, dtype=torch.uint8, device=device) for _ in range(2)]
@@ -171,17 +202,30 @@ class BatchFeeder:
         n = len(order)
         sel = order[(torch.arange(self.bs) + step * self.bs) % n]  # wrap the last partial batch
         if not self.cuda:
-            self._dev_x[slot].copy_(self.ds.images[sel])
+            if self.streaming:
+                self.ds.load_batch(sel, self._stage_x[slot])
+                self._dev_x[slot].copy_(self._stage_x[slot])
+            else:
+                self._dev_x[slot].copy_(self.ds.images[sel])
             self._dev_y[slot].copy_(self.ds.labels[sel])
             return
-        if step >= 2:
-            self._ready[slot].synchronize()          # pinned label staging of this slot is free again
+        if self._pending[slot]:
+            # the previous copy out of this slot's pinned staging (possibly issued by the PREVIOUS epoch) must
+            # have completed before the host rewrites it
+            self._ready[slot].synchronize()
+            self._pending[slot] = False
         torch.index_select(self.ds.labels, 0, sel, out=self._stage_y[slot])
+        if self.streaming:
+            self.ds.load_batch(sel, self._stage_x[slot])     # host decode of batch i+1 overlaps the GPU on batch i
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self._consumed[slot])
-            self.ops.gather_h2d_(self._dev_x[slot], self.ds.images, sel)
+            if self.streaming:
+                self._dev_x[slot].copy_(self._stage_x[slot], non_blocking=True)
+            else:
+                self.ops.gather_h2d_(self._dev_x[slot], self.ds.images, sel)
             self._dev_y[slot].copy_(self._stage_y[slot], non_blocking=True)
             self._ready[slot].record(self.copy_stream)
+        self._pending[slot] = True
 
     def epoch(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
         """Yields device tensors (uint8 NHWC images, int64 labels); batch i+1 copies while i computes."""

@@ -11,15 +11,17 @@ One round = what the reference's notebook cell 3 does once (N:233-272):
 * the pickle-file "network" and the server loop are replaced by the ciphertext all-reduce,
 * averaging is a sum in ciphertext space with 1/K folded into the decode scale.
 
-Roles: every rank holds the public context; the secret key lives with the key-holder role.
-In the multi-GPU benchmark every rank decrypts (a benchmark convenience mirroring the
-reference's single notebook that owns ``privatekey.pickle``).
+Roles: every rank holds the public context; the secret key is generated (OS entropy) and kept by
+the key-holder rank alone (default rank 0), which owns no chunk of the fused all-reduce, decrypts
+the aggregate and broadcasts the averaged plaintext model.
 """
 from __future__ import annotations
 
+import hashlib
 import json
 import math
 import os
+import secrets
 from typing import Dict, List, Optional
 
 import torch
@@ -47,24 +49,24 @@ class FederatedRunner:
         hp = cfg.he_params()
         self.ctx = CKKSContext(hp["n"], prime_bits=hp["prime_bits"], scale_bits=hp["scale_bits"],
                                device=self.device, sec=cfg.sec)
-        self.sk, self.pk = self.ctx.keygen(seed=cfg.seed)   # same seed on every rank -> same keys
-        # trust model: by default every client can decrypt the aggregate (nobody ever sees another client's
-        # plaintext update: the transport only carries ciphertext sums). With ``key_holder = r`` only rank r
-        # keeps the secret key, decrypts, and broadcasts the averaged plaintext model.
+        # Trust model (the reference's roles: the aggregator works with get_pk only, FLPyfhelin.py:370; get_sk is
+        # opened in decrypt alone, :284). The key holder generates the pair from OS entropy, keeps sk, and every
+        # other rank only ever receives pk. It owns no chunk of the fused all-reduce, so it never loads a peer's
+        # un-aggregated ciphertext; it decrypts the aggregate and broadcasts the averaged plaintext model.
         self.key_holder = int(cfg.key_holder) if world > 1 else -1
         if self.key_holder >= world:
             raise ValueError(f"key_holder {self.key_holder} is not a rank of this {world}-client federation")
-        self.has_sk = self.key_holder < 0 or rank == self.key_holder
-        if not self.has_sk:
-            self.sk = None
+        self.has_sk = world == 1 or self.key_holder < 0 or rank == self.key_holder
+        self._setup_keys()
         self.n_ct = self.ctx.num_ct(self.pack.numel, cfg.packing)
         self.ct_numel = self.n_ct * 2 * self.ctx.L * self.ctx.n
         kind = cfg.transport
         if self.device.type == "cpu" and kind == "fused":
             kind = "gloo" if world > 1 else "loopback"
         self.transport = make_transport(kind, self.ctx, self.ct_numel, world=world, group=group,
-                                        **({"algo": cfg.allreduce_algo, "timeout_s": cfg.timeout_s}
-                                           if kind == "fused" else {}))
+                                        **({"algo": cfg.allreduce_algo, "timeout_s": cfg.timeout_s,
+                                            "no_owner": self.key_holder} if kind == "fused" else {}))
+        self._pair_seeds = self._agree_pair_seeds() if (cfg.pairwise_masks and world > 1) else None
         # data: IID contiguous shard of a synthetic set (FLPyfhelin.py:75-78), 90/10 split (:85)
         # or, with ``dataset`` (e.g. ImageFolderDataset of this client's shard), real images: 10 % validate
         if dataset is not None:
@@ -87,6 +89,66 @@ class FederatedRunner:
         self.log = JsonlLogger(cfg.log_jsonl, rank)
         self.global_flat = self.pack.flat.clone()
         self.history: List[Dict] = []
+
+    # ------------------------------------------------------------------ keys and randomness
+    def _setup_keys(self) -> None:
+        cfg = self.cfg
+        if cfg.deterministic_crypto:
+            # bit-reproducible runs for tests: everything from the PUBLIC cfg.seed -- never in production
+            sk, self.pk = self.ctx.keygen(seed=cfg.seed)
+            self.sk = sk if self.has_sk else None
+            return
+        gen_rank = self.key_holder if self.key_holder >= 0 else 0
+        if self.world == 1 or self.rank == gen_rank:
+            sk, pk = self.ctx.keygen(seed=secrets.randbits(63))
+        else:
+            sk = torch.empty(self.ctx.L, self.ctx.n, dtype=torch.int64, device=self.device)
+            pk = torch.empty(2, self.ctx.L, self.ctx.n, dtype=torch.int64, device=self.device)
+        if self.world > 1:
+            dist.broadcast(pk, src=gen_rank, group=self.group)
+            if self.key_holder < 0:          # "every client can decrypt" mode: sk is handed out explicitly
+                dist.broadcast(sk, src=gen_rank, group=self.group)
+        self.pk = pk
+        self.sk = sk if self.has_sk else None
+
+    def _encrypt_seed(self) -> int:
+        """Fresh randomness for every encryption call. Re-running a round (resume, retry) must never reuse
+        (u, e0, e1) on different weights, and a seed derived from public values lets anybody strip the mask."""
+        if self.cfg.deterministic_crypto:
+            return (self.cfg.seed * 1_000_003 + self.round * 1009 + self.rank) & 0x7FFFFFFFFFFFFFFF
+        return secrets.randbits(63)
+
+    def _agree_pair_seeds(self):
+        """One 63-bit seed per peer. X25519 key agreement over the process group: only the two ends of a
+        pair can derive their seed. Returns (seeds, signs) with sign +1 towards higher ranks, -1 towards lower."""
+        peers = [j for j in range(self.world) if j != self.rank]
+        if self.cfg.deterministic_crypto:
+            def ps(i, j):
+                h = hashlib.sha256(f"hefl-pair-{self.cfg.seed}-{min(i, j)}-{max(i, j)}".encode()).digest()
+                return int.from_bytes(h[:8], "little") >> 1
+            seeds = [ps(self.rank, j) for j in peers]
+        else:
+            from cryptography.hazmat.primitives import serialization
+            from cryptography.hazmat.primitives.asymmetric.x25519 import X25519PrivateKey, X25519PublicKey
+
+            priv = X25519PrivateKey.generate()
+            pub = priv.public_key().public_bytes(serialization.Encoding.Raw, serialization.PublicFormat.Raw)
+            mine = torch.tensor(list(pub), dtype=torch.uint8, device=self.device)
+            allp = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(allp, mine, group=self.group)
+            seeds = []
+            for j in peers:
+                shared = priv.exchange(X25519PublicKey.from_public_bytes(bytes(allp[j].cpu().tolist())))
+                seeds.append(int.from_bytes(hashlib.sha256(b"hefl-pair" + shared).digest()[:8], "little") >> 1)
+        signs = [1 if j > self.rank else -1 for j in peers]
+        return seeds, signs
+
+    def _mask(self, data: torch.Tensor, chunk: int = 0) -> None:
+        if self._pair_seeds is None:
+            return
+        seeds, signs = self._pair_seeds
+        self.ctx.ops.pairwise_mask_(data, seeds, signs, (self.round * 4096 + chunk) & 0xFFFFFFFF, self.ctx.L,
+                                    self.ctx.logn, self.ctx.consts_cpu)
 
     # ------------------------------------------------------------------ stages
     def local_train(self, early_stopping: Optional[int] = None):
@@ -118,8 +180,10 @@ class FederatedRunner:
         self._agree_on_participants()
         with self.timer.stage("encrypt"):
             buf = self.transport.buffer(self.ct_numel)
-            seed = (self.cfg.seed * 1_000_003 + self.round * 1009 + self.rank) & 0x7FFFFFFFFFFFFFFF
-            return self.ctx.encrypt(self._my_update(), self.pk, seed=seed, packing=self.cfg.packing, out=buf)
+            ct = self.ctx.encrypt(self._my_update(), self.pk, seed=self._encrypt_seed(), packing=self.cfg.packing,
+                                  out=buf)
+            self._mask(ct.data)
+            return ct
 
     def aggregate(self, ct: CtBatch) -> CtBatch:
         with self.timer.stage("aggregate"):
@@ -158,7 +222,7 @@ class FederatedRunner:
         k = self._contributors()
         if k == 0:
             return
-        seed = (self.cfg.seed * 1_000_003 + self.round * 1009 + self.rank) & 0x7FFFFFFFFFFFFFFF
+        seed = self._encrypt_seed()
         # the three streams live as long as the runner: the caching allocator keeps one pool per stream, so
         # fresh streams every round meant fresh cudaMallocs (and cudaFree stalls) every round
         if getattr(self, "_pipe_streams", None) is None:
@@ -177,6 +241,7 @@ class FederatedRunner:
                 view = buf[c0 * per_ct: c1 * per_ct]
                 with torch.cuda.stream(s_enc):
                     ct = ctx.encrypt(vals, self.pk, seed=seed, packing=self.cfg.packing, out=view, ct_offset=c0)
+                    self._mask(ct.data, chunk=ci)
                     e = torch.cuda.Event(); e.record(s_enc); ev_enc.append(e)
                 with torch.cuda.stream(s_comm):
                     s_comm.wait_event(ev_enc[ci])
@@ -207,10 +272,14 @@ class FederatedRunner:
         plain_mean = None
         if self.cfg.debug_precision and not isinstance(self.transport, LoopbackTransport):
             # plaintext FedAvg oracle (SURVEY.md §5.5 "CKKS precision: max abs error vs plaintext FedAvg")
-            plain_mean = self.pack.flat.detach().clone().double()
+            # the oracle averages what the encrypted path averages: sitting-out clients contribute zeros and
+            # K is the agreed participant count
+            self._agree_on_participants()
+            plain_mean = self._my_update().detach().clone().double()
             if self.world > 1:
                 dist.all_reduce(plain_mean, op=dist.ReduceOp.SUM, group=self.group)
-                plain_mean /= self.world
+            kk = self._contributors()
+            plain_mean = plain_mean / kk if kk > 0 else None
         if pipelined is None:
             pipelined = self.device.type == "cuda" and self.n_ct > 512 and self.transport.name in ("fused", "nccl", "gloo")
         if pipelined:
@@ -280,20 +349,27 @@ class FederatedRunner:
 
     # ------------------------------------------------------------------ checkpoint / resume
     def save_checkpoint(self, path: str) -> None:
-        """Round index + model + optimiser + RNG so multi-round runs resume."""
-        torch.save({"round": self.round, "flat": self.pack.flat.detach().cpu(),
-                    "opt": self.trainer.state_dict(), "rng": torch.get_rng_state(),
-                    "cuda_rng": torch.cuda.get_rng_state(self.device) if self.device.type == "cuda" else None,
-                    "config": self.cfg.to_json()}, path)
+        """Round index + global model (rank 0 -> ``path``) and, PER RANK, optimiser moments, LR state and RNG
+        (``path.rank{r}``) so that a resumed multi-round run equals an uninterrupted one."""
+        if self.rank == 0:
+            torch.save({"round": self.round, "flat": self.pack.flat.detach().cpu(), "config": self.cfg.to_json()}, path)
+        torch.save({"round": self.round, "opt": self.trainer.state_dict(), "rng": torch.get_rng_state(),
+                    "cuda_rng": torch.cuda.get_rng_state(self.device) if self.device.type == "cuda" else None},
+                   f"{path}.rank{self.rank}")
 
     def load_checkpoint(self, path: str) -> None:
-        ck = torch.load(path, map_location="cpu", weights_only=False)
+        ck = torch.load(path, map_location="cpu", weights_only=True)      # tensors and plain containers only
         self.round = int(ck["round"])
         self.pack.load_flat(ck["flat"])
-        self.trainer.load_state_dict(ck["opt"])
-        torch.set_rng_state(ck["rng"])
-        if ck.get("cuda_rng") is not None and self.device.type == "cuda":
-            torch.cuda.set_rng_state(ck["cuda_rng"], self.device)
+        mine = f"{path}.rank{self.rank}"
+        if os.path.exists(mine):
+            st = torch.load(mine, map_location="cpu", weights_only=True)
+            self.trainer.load_state_dict(st["opt"])
+            torch.set_rng_state(st["rng"])
+            if st.get("cuda_rng") is not None and self.device.type == "cuda":
+                torch.cuda.set_rng_state(st["cuda_rng"], self.device)
+        else:                                       # no state of this rank (e.g. a different world size): start it fresh
+            self.trainer.reset_optimizer()
         if self.trainer.engine is not None:
             self.trainer.engine.after_restore()
 

@@ -48,16 +48,21 @@ class FusedTransport(Transport):
 
     def __init__(self, ctx: CKKSContext, max_numel: int, group: Optional[dist.ProcessGroup] = None,
                  algo: str = "auto", blocks: int = 0, threads: int = 512, timeout_s: float = 20.0,
-                 backend: str = "auto"):
+                 backend: str = "auto", no_owner: int = -1):
         self.ops = _ext.ops()
         self.ctx = ctx
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.max_numel = int(max_numel + (max_numel & 1))
+        self.max_numel = int((max_numel + 3) // 4 * 4)
         self.threads = threads
-        self.max_blocks = 128
+        # one CTA per SM: the kernel is a copy engine, a second CTA per SM only adds flag traffic
+        self.max_blocks = (torch.cuda.get_device_properties(ctx.device).multi_processor_count
+                           if ctx.device.type == "cuda" else 128)
         self.blocks = blocks
+        # rank that must never read un-aggregated ciphertext (the secret-key holder): it owns no chunk
+        self.no_owner = int(no_owner) if self.world > 1 else -1
+        self.stats = torch.zeros(1, dtype=torch.int32, device=ctx.device)
         self.timeout_ms = int(timeout_s * 1000)
         self.sym = SymmetricBuffer(self.max_numel, torch.int64, ctx.device, group, backend)
         self.sig = SymmetricBuffer(2 * self.max_blocks * max(self.world, 1) + 64, torch.int32,
@@ -77,8 +82,8 @@ class FusedTransport(Transport):
             return self.algo
         if self.world == 1:
             return "two_shot"
-        if nbytes <= 256 * 1024:
-            return "one_shot"
+        if nbytes <= 256 * 1024 and self.no_owner < 0:
+            return "one_shot"          # every rank reads everything: never with a key holder
         if self.sym.mc_ptr and os.environ.get("HEFL_USE_MULTIMEM", "0") == "1":
             return "multimem"
         return "two_shot"
@@ -86,14 +91,17 @@ class FusedTransport(Transport):
     def pick_blocks(self, numel: int, algo: str) -> int:
         if self.blocks:
             return min(self.blocks, self.max_blocks)
-        work = numel // 2 if algo == "one_shot" else max(1, numel // 2 // self.world)
+        owners = self.world - (1 if self.no_owner >= 0 else 0)
+        work = numel // 4 if algo == "one_shot" else max(1, numel // 4 // max(1, owners))   # 32-byte quads
         return max(1, min(self.max_blocks, (work + self.threads - 1) // self.threads))
 
     def allreduce(self, data: torch.Tensor) -> torch.Tensor:
         numel = data.numel()
         base = self.sym.tensor
         off = data.data_ptr() - base.data_ptr()
-        inside = 0 <= off and off + numel * 8 <= self.max_numel * 8 and off % 16 == 0
+        if numel % 4:
+            raise ValueError("ciphertext word count must be a multiple of 4")
+        inside = 0 <= off and off + numel * 8 <= self.max_numel * 8 and off % 32 == 0
         if not inside:
             # caller did not encrypt in place: stage into the symmetric buffer
             self.buffer(numel).copy_(data.reshape(-1))
@@ -107,9 +115,15 @@ class FusedTransport(Transport):
                                 self.sym.mc_ptr + off if self.sym.mc_ptr else 0, out, self.status,
                                 self.ctx.consts_cpu, numel, data.shape[-2], self.ctx.logn,
                                 self.rank, self.world, ALGOS[algo], blocks, self.threads,
-                                self.timeout_ms)
+                                self.timeout_ms, self.no_owner if algo != "one_shot" else -1, self.stats)
         src = self.out if algo == "one_shot" else base
         return src[e0:e0 + numel].view(data.shape)
+
+    def peer_load_steps(self) -> int:
+        """32-byte peer-load steps this rank has issued since the last call (0 for a key holder)."""
+        n = int(self.stats.item())
+        self.stats.zero_()
+        return n
 
     def check_status(self) -> None:
         """Raises if a bounded spin-wait timed out in a previous launch (failure detection)."""
@@ -195,6 +209,7 @@ def make_transport(kind: str, ctx: CKKSContext, max_numel: int, world: int = 1,
                    group: Optional[dist.ProcessGroup] = None, **kw) -> Transport:
     if kind == "fused":
         return FusedTransport(ctx, max_numel, group, **kw)
+    kw.pop("no_owner", None)
     if kind in ("nccl", "gloo", "collective"):
         return CollectiveTransport(ctx, max_numel, group)
     if kind == "loopback":

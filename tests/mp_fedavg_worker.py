@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--rounds", type=int, default=2)
     ap.add_argument("--key-holder", type=int, default=-1)
     ap.add_argument("--drop-rank", type=int, default=-1)
+    ap.add_argument("--masks", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
     gpu = args.backend == "nccl"
@@ -43,9 +44,14 @@ def main():
                        device="cuda" if gpu else "cpu", debug_poison=True)   # stale words would break the cross-check
     cfg.key_holder = args.key_holder
     cfg.allow_dropouts = args.drop_rank >= 0
+    cfg.pairwise_masks = args.masks
     run = FederatedRunner(cfg, rank=rank, world=world, device=device)
     if args.key_holder >= 0:
         assert (run.sk is not None) == (rank == args.key_holder), "only the key holder may keep the secret key"
+    # every rank must hold the SAME public key (generated once, from OS entropy, by the key holder / rank 0)
+    pk0 = run.pk.clone()
+    dist.broadcast(pk0, src=0)
+    assert torch.equal(pk0, run.pk), "public keys differ between ranks"
     worst = 0.0
     for rnd in range(args.rounds):
         run.local_train()
@@ -57,7 +63,13 @@ def main():
             gathered = [g for r, g in enumerate(gathered) if r != args.drop_rank]
         plain_mean = torch.stack(gathered).mean(0)
         ct = run.encrypt_update()
+        if hasattr(run.transport, "peer_load_steps"):
+            run.transport.peer_load_steps()
         agg = run.aggregate(ct)
+        if hasattr(run.transport, "peer_load_steps") and args.key_holder >= 0 and world > 1:
+            steps = run.transport.peer_load_steps()
+            # the key holder owns no chunk: it must not have loaded a single word of a peer's un-aggregated data
+            assert (steps == 0) == (rank == args.key_holder), f"rank {rank}: {steps} peer-load steps"
         run.decrypt_apply(agg)
         run.guard_finite()
         if hasattr(run.transport, "check_status"):

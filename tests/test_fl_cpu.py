@@ -74,7 +74,7 @@ def test_debug_poison_between_rounds_keeps_results_identical():
     from hefl_b200.fl import FederatedRunner
 
     def run(poison):
-        cfg = _cfg(local_epochs=1, steps_per_epoch=2, clients=1, seed=3, debug_poison=poison)
+        cfg = _cfg(local_epochs=1, steps_per_epoch=2, clients=1, seed=3, debug_poison=poison, deterministic_crypto=True)
         r = FederatedRunner(cfg, device=torch.device("cpu"))
         for _ in range(2):
             r.run_round(check=True)

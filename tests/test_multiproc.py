@@ -53,6 +53,12 @@ def test_federated_round_with_a_dropped_client_gloo():
     assert rep["world"] == 2 and rep["max_abs_err"] < 1e-5
 
 
+def test_federated_round_with_pairwise_masks_gloo():
+    """pairwise_masks: X25519-agreed PRG masks on every client's ciphertext cancel in the all-reduce."""
+    rep = _run(2, "gloo", 29647, ["--rounds", "2", "--masks", "--key-holder", "0"], worker=FED_WORKER)
+    assert rep["world"] == 2 and rep["max_abs_err"] < 1e-5
+
+
 def test_federated_round_with_a_single_key_holder_gloo():
     """key_holder=1: only rank 1 keeps the secret key, decrypts and broadcasts; same result on every rank."""
     rep = _run(2, "gloo", 29643, ["--rounds", "2", "--key-holder", "1"], worker=FED_WORKER)
@@ -66,4 +72,17 @@ def test_federated_round_across_gpus(nproc, model):
     if torch.cuda.device_count() < nproc:
         pytest.skip(f"needs {nproc} GPUs")
     rep = _run(nproc, "nccl", 29650 + nproc, ["--rounds", "2", "--model", model], worker=FED_WORKER)
+    assert rep["transport"] == "fused" and rep["max_abs_err"] < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.multigpu
+@pytest.mark.parametrize("nproc", [2, 8])
+def test_key_holder_never_loads_peer_ciphertext_across_gpus(nproc):
+    """Default trust model on the fused transport: rank 0 generates the keys, owns no chunk of the all-reduce
+    (its peer-load counter stays 0 while every other rank's is positive), decrypts and broadcasts; with masks."""
+    if torch.cuda.device_count() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    rep = _run(nproc, "nccl", 29670 + nproc, ["--rounds", "2", "--model", "medcnn", "--key-holder", "0", "--masks"],
+               worker=FED_WORKER)
     assert rep["transport"] == "fused" and rep["max_abs_err"] < 1e-5

@@ -218,11 +218,30 @@ allreduce_modq_kernel(const __grid_constant__ AllReduceArgs a) {
   block_barrier(a, 1, deadline);
 }
 
+template <int ALGO>
+static void launch_allreduce(const AllReduceArgs& args, int blocks, int threads, cudaStream_t st) {
+  // Even grids go out as clusters of two CTAs: a cluster takes both SMs of a TPC, so a small grid (the
+  // SM-partitioned pipeline gives the collective ~24 SMs) does not leave half-used TPCs that the cluster
+  // kernels of encrypt / decrypt could no longer be placed on.
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (blocks % 2 == 0) ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, allreduce_modq_kernel<ALGO>, args);
+}
+
 void allreduce_modq(const AllReduceArgs& args, int algo, int blocks, int threads, cudaStream_t st) {
   switch (algo) {
-    case 0: allreduce_modq_kernel<0><<<blocks, threads, 0, st>>>(args); break;
-    case 1: allreduce_modq_kernel<1><<<blocks, threads, 0, st>>>(args); break;
-    default: allreduce_modq_kernel<2><<<blocks, threads, 0, st>>>(args); break;
+    case 0: launch_allreduce<0>(args, blocks, threads, st); break;
+    case 1: launch_allreduce<1>(args, blocks, threads, st); break;
+    default: launch_allreduce<2>(args, blocks, threads, st); break;
   }
   hefl::cuda::note_launch();
 }

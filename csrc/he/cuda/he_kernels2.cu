@@ -15,6 +15,7 @@
 // Replaces the per-scalar HE.encryptFrac / decryptFrac loops (FLPyfhelin.py:216-217, :294-295).
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <stdexcept>
 #include <string>
@@ -544,15 +545,24 @@ CUtensorMap rows128_map(const void* ptr, uint64_t bytes, uint32_t box_rows) {
   return m;
 }
 
-int grid_ctas() {
+// Per-role CTA budgets (0 = every SM). The persistent kernels take one SM per CTA; when the pipelined FedAvg
+// runs encrypt, the ciphertext all-reduce and decrypt on three streams they only overlap if each leaves SMs to
+// the others, so the runner partitions the chip (set_cta_limits) instead of letting three full-chip kernels queue.
+int g_limit[3] = {0, 0, 0};   // 0 ntt, 1 encrypt, 2 decrypt
+
+int sm_count() {
   static int n = 0;
   if (!n) {
-    int dev = 0, sms = 0;
+    int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    n = sms & ~1;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
   }
   return n;
+}
+int grid_ctas(int role = 0) {
+  int n = sm_count() & ~1;
+  if (g_limit[role] > 0 && g_limit[role] < n) n = g_limit[role] & ~1;
+  return n < 2 ? 2 : n;
 }
 
 template <class K>
@@ -609,7 +619,7 @@ void launch_encrypt2(const EncArgs& a, cudaStream_t st) {
   const CUtensorMap tmap = rows128_map(a.tw2, (uint64_t)a.L * 2 * N * 16, tw_rows(LOGN) / 2);
   auto k = encrypt2_kernel<LOGN>;
   set_smem(k, Smem<LOGN, 2>::kTotal);
-  k<<<grid_ctas(), kThreads, Smem<LOGN, 2>::kTotal, st>>>(tmap, a);
+  k<<<grid_ctas(1), kThreads, Smem<LOGN, 2>::kTotal, st>>>(tmap, a);
 }
 
 template <int LOGN, unsigned CORR>
@@ -618,7 +628,7 @@ void launch_decrypt2(const DecArgs& a, int Ltab, cudaStream_t st) {
   const CUtensorMap tmap = rows128_map(a.tw2, (uint64_t)Ltab * 2 * N * 16, tw_rows(LOGN) / 2);
   auto k = decrypt2_kernel<LOGN, CORR>;
   set_smem(k, Smem<LOGN, 1>::kTotal);
-  k<<<grid_ctas(), kThreads, Smem<LOGN, 1>::kTotal, st>>>(tmap, a);
+  k<<<grid_ctas(2), kThreads, Smem<LOGN, 1>::kTotal, st>>>(tmap, a);
 }
 
 template <int LOGN>
@@ -644,7 +654,16 @@ void shoup_pairs(const uint64_t* x, uint64_t* out, int64_t rows, int L, int n, c
 
 // The fast path needs every prime below 2^58 (lazy forward butterflies without correction), at
 // most as many limbs as clusters, and 1024 <= N <= 16384.
-bool ntt2_supported(int logn, int L, int qbits) { return logn >= 10 && logn <= 14 && qbits <= 58 && L <= grid_ctas() / 2; }
+bool ntt2_supported(int logn, int L, int qbits) {
+  const int g = std::min(grid_ctas(0), std::min(grid_ctas(1), grid_ctas(2)));
+  return logn >= 10 && logn <= 14 && qbits <= 58 && L <= g / 2;
+}
+
+void set_cta_limits(int ntt, int enc, int dec) {
+  g_limit[0] = ntt;
+  g_limit[1] = enc;
+  g_limit[2] = dec;
+}
 
 bool ntt2(uint64_t* data, int64_t rows, int L, int logn, const uint64_t* tw2, const uint64_t* consts, int qbits,
           bool inverse, cudaStream_t st) {
@@ -672,7 +691,7 @@ bool encrypt2(const int64_t* msg, const uint64_t* pkx, uint64_t* ct, int64_t C, 
     // ciphertexts of the medical CNN) the one-CTA-per-(ciphertext, limb) kernel fills the GPU
     // better (measured 0.107 vs 0.131 ms at n = 4096, L = 3, C = 109).
     const int64_t units = (C * (1ll << logn) + 8191) / 8192;
-    const int64_t workers = (grid_ctas() / 2 / L) * 2;
+    const int64_t workers = (grid_ctas(1) / 2 / L) * 2;
     if (units < 2 * workers) return false;
   }
   const EncArgs a{msg, pkx, ct, tw2, consts, msg_scale, seed, ct_offset, L, C};

@@ -93,9 +93,11 @@ struct Limb {
   uint64_t ninv, ninv_p;
 };
 
-template <int STAGE>
+// G = true: every stage reads the table from global memory (kernels that walk over several limbs per
+// CTA -- rescale, key switch -- have no room for one resident table per limb; the tables stay in L2).
+template <int STAGE, bool G = false>
 __device__ __forceinline__ void tw_pair(const Limb& T, uint32_t ti, uint64_t& w, uint64_t& wp) {
-  if constexpr (STAGE < kTwLog) {
+  if constexpr (STAGE < kTwLog && !G) {
     lds128(T.tw + swz(ti << 4), w, wp);
   } else {
     ldg128(T.twg + 2 * (size_t)ti, w, wp);
@@ -114,7 +116,7 @@ __device__ __forceinline__ uint64_t full_reduce(uint64_t x, const Limb& T) {
 // R forward (Cooley-Tukey) stages ST .. ST+R-1 on the 2^R values of one group held in registers.
 // `high` is the group's index above the stride (its twiddle selector). No correction: inputs
 // below B*q give outputs below (B + 2R)*q.
-template <int ST, int R>
+template <int ST, int R, bool G = false>
 __device__ __forceinline__ void fwd_butterflies(uint64_t (&x)[1 << R], uint32_t high, const Limb& T) {
   constexpr int E = 1 << R;
   const uint32_t idx0 = (1u << ST) + high;
@@ -127,7 +129,7 @@ __device__ __forceinline__ void fwd_butterflies(uint64_t (&x)[1 << R], uint32_t 
         uint64_t W, Wp;
         const uint32_t ti = (idx0 << u) + (uint32_t)(k >> (R - u));
         // the stage is ST + u: a compile-time value once the loop is unrolled
-        if (ST + u < kTwLog) tw_pair<0>(T, ti, W, Wp); else tw_pair<kTwLog>(T, ti, W, Wp);
+        if (ST + u < kTwLog) tw_pair<0, G>(T, ti, W, Wp); else tw_pair<kTwLog, G>(T, ti, W, Wp);
         const uint64_t Q = mul_shoup_lazy(x[k + half], W, Wp, T.q);
         const uint64_t X = x[k];
         x[k] = X + Q;
@@ -139,7 +141,7 @@ __device__ __forceinline__ void fwd_butterflies(uint64_t (&x)[1 << R], uint32_t 
 
 // R inverse (Gentleman-Sande) stages ST+R-1 .. ST. `bound` (compile time, in units of q) bounds
 // the inputs; outputs are below bound * 2^R * q. Twiddles are the inverse table (same indexing).
-template <int ST, int R, int BOUND>
+template <int ST, int R, int BOUND, bool G = false>
 __device__ __forceinline__ void inv_butterflies(uint64_t (&x)[1 << R], uint32_t high, const Limb& T) {
   constexpr int E = 1 << R;
   const uint32_t idx0 = (1u << ST) + high;
@@ -153,7 +155,7 @@ __device__ __forceinline__ void inv_butterflies(uint64_t (&x)[1 << R], uint32_t 
       if ((k & half) == 0) {
         uint64_t W, Wp;
         const uint32_t ti = (idx0 << u) + (uint32_t)(k >> (R - u));
-        if (ST + u < kTwLog) tw_pair<0>(T, ti, W, Wp); else tw_pair<kTwLog>(T, ti, W, Wp);
+        if (ST + u < kTwLog) tw_pair<0, G>(T, ti, W, Wp); else tw_pair<kTwLog, G>(T, ti, W, Wp);
         const uint64_t U = x[k], V = x[k + half];
         x[k] = U + V;
         x[k + half] = mul_shoup_lazy(U + (bq - V), W, Wp, T.q);
@@ -218,7 +220,7 @@ __device__ __forceinline__ void group_store(uint32_t buf, const Geo<LOGN, P>& G,
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
 
 // One in-place shared-memory forward pass over the whole unit. Ends with a compute barrier.
-template <int LOGN, int P>
+template <int LOGN, int P, bool TG = false>
 __device__ __forceinline__ void fwd_pass_smem(uint32_t buf, const Limb& T) {
   using GG = Geo<LOGN, P>;
 #pragma unroll 1
@@ -226,7 +228,7 @@ __device__ __forceinline__ void fwd_pass_smem(uint32_t buf, const Limb& T) {
     const GG G(threadIdx.x + j * kThreads);
     uint64_t x[GG::E];
     group_load<LOGN, P>(buf, G, x);
-    fwd_butterflies<GG::ST, GG::R>(x, G.high, T);
+    fwd_butterflies<GG::ST, GG::R, TG>(x, G.high, T);
     group_store<LOGN, P>(buf, G, x);
   }
   compute_sync();
@@ -245,7 +247,7 @@ __host__ __device__ constexpr int inv_bound_in(int P, int B0, unsigned corr) {
   return b;
 }
 
-template <int LOGN, int P, int B0, unsigned CORR>
+template <int LOGN, int P, int B0, unsigned CORR, bool TG = false>
 __device__ __forceinline__ void inv_pass_smem(uint32_t buf, const Limb& T) {
   using GG = Geo<LOGN, P>;
   constexpr int BIN = inv_bound_in<LOGN>(P, B0, CORR);
@@ -258,7 +260,7 @@ __device__ __forceinline__ void inv_pass_smem(uint32_t buf, const Limb& T) {
 #pragma unroll
       for (int k = 0; k < GG::E; ++k) x[k] = lazy_reduce(x[k], T);
     }
-    inv_butterflies<GG::ST, GG::R, BIN>(x, G.high, T);
+    inv_butterflies<GG::ST, GG::R, BIN, TG>(x, G.high, T);
     group_store<LOGN, P>(buf, G, x);
   }
   compute_sync();

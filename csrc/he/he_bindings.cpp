@@ -415,7 +415,53 @@ Tensor digit_extract(const Tensor& x, int64_t shift, int64_t bits) {
   return out;
 }
 
+// ct [C,2,lvl,N] -> round(ct / q_last) [C,2,lvl-1,N] in one launch. Returns an empty tensor when the fused kernel
+// does not cover the parameters (CPU tensors, N >= 16384, primes >= 2^58): the caller runs the reference loop.
+Tensor rescale_fused(const Tensor& ct, const Tensor& tables, const Tensor& consts, const Tensor& consts_cpu, int64_t logn) {
+  TORCH_CHECK(ct.dim() == 4 && ct.size(1) == 2 && ct.is_contiguous(), "ct must be contiguous [C,2,lvl,N]");
+  const int64_t C = ct.size(0), lvl = ct.size(2), n = ct.size(3);
+  if (!ct.is_cuda() || !fast_path_enabled() || lvl < 2 || tables.size(0) < lvl) return Tensor();
+  const TableExt& te = table_ext(tables, consts);
+  const uint64_t* cc = u64(consts_cpu);
+  const uint64_t ql = cc[(lvl - 1) * 8];
+  std::vector<uint64_t> inv(lvl), invp(lvl);
+  for (int64_t j = 0; j + 1 < lvl; ++j) {
+    const uint64_t qj = cc[j * 8];
+    inv[j] = hefl::host::inv_mod(ql % qj, qj);
+    invp[j] = (uint64_t)(((unsigned __int128)inv[j] << 64) / qj);
+  }
+  Tensor out = at::empty({C, 2, lvl - 1, n}, ct.options());
+  if (!hefl::cuda::rescale2(u64(ct), u64(out), C, (int)lvl, (int)logn, u64(te.tw2), u64(consts), inv.data(), invp.data(),
+                            te.qbits, cur_stream()))
+    return Tensor();
+  return out;
+}
+
+// acc [C,2,lvl,N] (holding d0, d1) += key switch of d2 given in COEFFICIENT form [C,lvl,N]; evk [E,2,Ltab,N].
+bool keyswitch_fused_(Tensor acc, const Tensor& coef, const Tensor& evk, at::IntArrayRef ndig, at::IntArrayRef first,
+                      int64_t digit_bits, const Tensor& tables, const Tensor& consts, int64_t logn) {
+  if (!acc.is_cuda() || !fast_path_enabled()) return false;
+  TORCH_CHECK(acc.dim() == 4 && acc.is_contiguous() && coef.is_contiguous() && evk.is_contiguous(), "contiguous tensors expected");
+  const int64_t C = acc.size(0), lvl = acc.size(2);
+  TORCH_CHECK((int64_t)ndig.size() == lvl && (int64_t)first.size() == lvl, "one digit count per limb");
+  const TableExt& te = table_ext(tables, consts);
+  std::vector<int> nd(ndig.begin(), ndig.end()), fi(first.begin(), first.end());
+  return hefl::cuda::keyswitch2(u64(coef), u64(evk), u64(acc), C, (int)lvl, (int)tables.size(0), (int)logn, (int)digit_bits,
+                                nd.data(), fi.data(), u64(te.tw2), u64(consts), te.qbits, cur_stream());
+}
+
+// (a0 b0, a0 b1 + a1 b0) as a ciphertext-shaped tensor and a1 b1, element-wise (CUDA only).
+std::tuple<Tensor, Tensor> ct_tensor(const Tensor& a, const Tensor& b, const Tensor& consts) {
+  TORCH_CHECK(a.is_cuda() && a.dim() == 4 && a.sizes() == b.sizes() && a.is_contiguous() && b.is_contiguous(), "bad operands");
+  const int64_t C = a.size(0), lvl = a.size(2), n = a.size(3);
+  Tensor d01 = at::empty_like(a);
+  Tensor d2 = at::empty({C, lvl, n}, a.options());
+  hefl::cuda::ct_tensor(u64(a), u64(b), u64(d01), u64(d2), C, (int)lvl, (int)n, u64(consts), cur_stream());
+  return {d01, d2};
+}
+
 int64_t launch_count() { return (int64_t)hefl::cuda::launch_count(); }
+void set_he_cta_limits(int64_t ntt, int64_t enc, int64_t dec) { hefl::cuda::set_cta_limits((int)ntt, (int)enc, (int)dec); }
 
 }  // namespace
 
@@ -441,5 +487,9 @@ TORCH_LIBRARY_FRAGMENT(hefl, m) {
   m.def("bfv_scale_round(Tensor x, int q, int p) -> Tensor", &bfv_scale_round);
   m.def("digit_extract(Tensor x, int shift, int bits) -> Tensor", &digit_extract);
   m.def("shoup_pairs(Tensor x, Tensor consts, int L) -> Tensor", &shoup_pairs);
+  m.def("rescale_fused(Tensor ct, Tensor tables, Tensor consts, Tensor consts_cpu, int logn) -> Tensor", &rescale_fused);
+  m.def("keyswitch_fused_(Tensor(a!) acc, Tensor coef, Tensor evk, int[] ndig, int[] first, int digit_bits, Tensor tables, Tensor consts, int logn) -> bool", &keyswitch_fused_);
+  m.def("ct_tensor(Tensor a, Tensor b, Tensor consts) -> (Tensor, Tensor)", &ct_tensor);
   m.def("launch_count() -> int", &launch_count);
+  m.def("set_he_cta_limits(int ntt, int enc, int dec) -> ()", &set_he_cta_limits);
 }

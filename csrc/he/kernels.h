@@ -51,6 +51,8 @@ void digit_extract(const uint64_t* x, int64_t rows, int n, int shift, int bits, 
 // skx: [L][N][2] (s, s'); qbits: bit length of the largest prime. Each returns false (and
 // launches nothing) when the parameters are outside the fast path: the caller falls back.
 bool ntt2_supported(int logn, int L, int qbits);
+// CTA budgets of the persistent kernels (0 = all SMs): lets encrypt / all-reduce / decrypt share the chip.
+void set_cta_limits(int ntt, int enc, int dec);
 bool ntt2(uint64_t* data, int64_t rows, int L, int logn, const uint64_t* tw2, const uint64_t* consts, int qbits,
           bool inverse, cudaStream_t st);
 bool encrypt2(const int64_t* msg, const uint64_t* pkx, uint64_t* ct, int64_t C, int L, int logn, const uint64_t* tw2,
@@ -58,6 +60,17 @@ bool encrypt2(const int64_t* msg, const uint64_t* pkx, uint64_t* ct, int64_t C, 
               cudaStream_t st);
 bool decrypt2(const uint64_t* ct, const uint64_t* skx, uint64_t* out, int64_t C, int Lct, int k, int logn,
               const uint64_t* tw2, const uint64_t* consts, int Ltab, int qbits, cudaStream_t st);
+
+// ---- fused evaluation kernels (csrc/he/cuda/he_eval2.cu); false = outside the fast path, nothing launched ----
+// inv / inv_p: host arrays, q_last^-1 mod q_j and its Shoup companion for j < lvl - 1.
+bool rescale2(const uint64_t* ct, uint64_t* out, int64_t C, int lvl, int logn, const uint64_t* tw2, const uint64_t* consts,
+              const uint64_t* inv, const uint64_t* inv_p, int qbits, cudaStream_t st);
+// acc [C][2][lvl][N] += sum_{i,k} NTT(digit_{i,k}(coef)) * evk[first[i] + k]; ndig / first: host arrays of lvl ints.
+bool keyswitch2(const uint64_t* coef, const uint64_t* evk, uint64_t* acc, int64_t C, int lvl, int Ltab, int logn,
+                int digit_bits, const int* ndig, const int* first, const uint64_t* tw2, const uint64_t* consts, int qbits,
+                cudaStream_t st);
+void ct_tensor(const uint64_t* A, const uint64_t* B, uint64_t* d01, uint64_t* d2, int64_t C, int lvl, int n,
+               const uint64_t* consts, cudaStream_t st);
 
 // rows [rows][n] (row r belongs to limb r % L) -> [rows][n][2] = (x, floor(x * 2^64 / q))
 void shoup_pairs(const uint64_t* x, uint64_t* out, int64_t rows, int L, int n, const uint64_t* consts,

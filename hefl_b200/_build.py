@@ -39,6 +39,7 @@ NVCC_FLAGS = [
 CUDA_SOURCES = [
     "he/cuda/he_kernels.cu",
     "he/cuda/he_kernels2.cu",
+    "he/cuda/he_eval2.cu",
     "comm/allreduce_modq.cu",
     "nn/conv_tcgen05.cu",
     "nn/nn_kernels.cu",

@@ -187,9 +187,9 @@ class Pyfhel:
         if self._sk is None:
             raise RuntimeError("relinKeyGen needs the secret key")
         if self._scheme != ENC_CKKS:
-            self._rlk = ("bfv-relin", int(bitCount), int(size))   # kept for repr/API parity
+            self._rlk = self._ctx.relin_keygen(self._sk, seed=secrets.randbits(63), bit_count=int(bitCount), size=int(size))
             return
-        self._rlk = self._ctx.relin_keygen(self._sk, seed=self._enc_seed, digit_bits=max(1, min(int(bitCount), 30)))
+        self._rlk = self._ctx.relin_keygen(self._sk, seed=secrets.randbits(63), digit_bits=max(1, min(int(bitCount), 30)))
 
     def rotateKeyGen(self, *a, **k):
         raise NotImplementedError("rotations are not used by the reference (repr shows rtk:-)")
@@ -334,11 +334,11 @@ class Pyfhel:
         return self._ctx.mul_plain(x.unsqueeze(0), v)[0], 1.0
 
     def _mul_ct(self, a: PyCtxt, b: PyCtxt):
-        if a._encoding != ENC_CKKS:
-            raise NotImplementedError("ciphertext x ciphertext is provided for the CKKS scheme")
         if self._rlk is None:
             raise RuntimeError("relinKeyGen() must be called before PyCtxt * PyCtxt")
         x, y = self._pair(a, b)
+        if a._encoding != ENC_CKKS:
+            return self._ctx.multiply(x.unsqueeze(0), y.unsqueeze(0), self._rlk)[0], 1.0
         out = self._ctx.multiply(CtBatch(x, a._scale, a._nvals), CtBatch(y, b._scale, b._nvals), self._rlk)
         return out.data, out.scale
 

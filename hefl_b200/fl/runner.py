@@ -232,31 +232,77 @@ class FederatedRunner:
         for st in (s_enc, s_comm, s_dec):
             st.wait_stream(cur)
         buf = self.transport.buffer(self.ct_numel)
+        # The three stages only overlap if they fit on the chip together: encrypt / decrypt are persistent
+        # one-CTA-per-SM kernels and the all-reduce is a copy engine that saturates NVLink from a few SMs, so the
+        # SMs are partitioned for the duration of the pipeline (measured on ResNet-18, 8 GPUs: see profiles/).
+        split = None
+        if self.world > 1 and dev.type == "cuda" and self.transport.name == "fused":
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            env = os.environ.get("HEFL_PIPE_SPLIT")
+            if env:
+                split = tuple(int(v) for v in env.split(","))
+            else:
+                ar = 24
+                dec = 28 if self.has_sk else 0
+                split = (sms - ar - dec, dec, ar)
+            if min(split[0], split[2]) >= 2 * ctx.L and split[0] + split[1] + split[2] <= sms:
+                ctx.ops.set_he_cta_limits(0, split[0], split[1])
+                saved_blocks, self.transport.blocks = self.transport.blocks, split[2]
+            else:
+                split = None
+        timeline = [] if os.environ.get("HEFL_TIMELINE") else None
+
+        def mark(stream):
+            e = torch.cuda.Event(enable_timing=timeline is not None)
+            e.record(stream)
+            return e
+
         with self.timer.stage("fedavg_pipelined"):
             ev_enc, ev_comm = [], []
             chunks = [(c0, min(n_ct, c0 + chunk_cts)) for c0 in range(0, n_ct, chunk_cts)]
-            reduced = []
+            t_origin = mark(cur) if timeline is not None else None
             for ci, (c0, c1) in enumerate(chunks):
                 vals = flat[c0 * vpc: min(flat.numel(), c1 * vpc)]
                 view = buf[c0 * per_ct: c1 * per_ct]
+                rec = {"chunk": ci}
                 with torch.cuda.stream(s_enc):
+                    if timeline is not None:
+                        rec["enc0"] = mark(s_enc)
                     ct = ctx.encrypt(vals, self.pk, seed=seed, packing=self.cfg.packing, out=view, ct_offset=c0)
                     self._mask(ct.data, chunk=ci)
-                    e = torch.cuda.Event(); e.record(s_enc); ev_enc.append(e)
+                    ev_enc.append(mark(s_enc))
                 with torch.cuda.stream(s_comm):
                     s_comm.wait_event(ev_enc[ci])
+                    if timeline is not None:
+                        rec["ar0"] = mark(s_comm)
                     data = self.transport.allreduce(ct.data)
-                    e = torch.cuda.Event(); e.record(s_comm); ev_comm.append(e)
-                reduced.append((c0, c1, data, ct))
+                    ev_comm.append(mark(s_comm))
                 with torch.cuda.stream(s_dec):
                     s_dec.wait_event(ev_comm[ci])
-                    from ..he.context import CtBatch as _CB
+                    if timeline is not None:
+                        rec["dec0"] = mark(s_dec)
                     if self.has_sk:
-                        avg = ctx.decrypt(_CB(data, ct.scale, ct.nvals, ct.packing), self.sk, divide_by=k)
+                        avg = ctx.decrypt(CtBatch(data, ct.scale, ct.nvals, ct.packing), self.sk, divide_by=k)
                         out[c0 * vpc: c0 * vpc + avg.numel()].copy_(avg)
+                    if timeline is not None:
+                        rec["dec1"] = mark(s_dec)
+                if timeline is not None:
+                    rec["enc1"], rec["ar1"] = ev_enc[ci], ev_comm[ci]
+                    timeline.append(rec)
             cur.wait_stream(s_dec)
             cur.wait_stream(s_comm)
             cur.wait_stream(s_enc)
+            if split is not None:
+                ctx.ops.set_he_cta_limits(0, 0, 0)
+                self.transport.blocks = saved_blocks
+            if timeline is not None:
+                torch.cuda.synchronize(dev)
+                rows = [{"chunk": r["chunk"], **{k: round(t_origin.elapsed_time(r[k]), 4) for k in r if k != "chunk"}}
+                        for r in timeline]
+                if self.rank == 0:
+                    with open(os.environ["HEFL_TIMELINE"], "w") as f:
+                        json.dump({"world": self.world, "n_ct": n_ct, "chunk_cts": chunk_cts, "sm_split_enc_dec_ar": split,
+                                   "unit": "ms since the start of the FedAvg stage", "chunks": rows}, f, indent=1)
             if self.key_holder >= 0:
                 dist.broadcast(out, src=self.key_holder, group=self.group)
             self.pack.load_flat(out)

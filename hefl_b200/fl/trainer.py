@@ -75,6 +75,10 @@ class LocalTrainer:
         self.graph_launches = [0, 0]      # our kernels inside one train / eval graph
         self.replayed_launches = 0        # ... summed over replays (bench.py gpu_launches)
         self.engine = None
+        if self.backend == "cudnn" and self.cuda:
+            # the library arm gets what a tuned PyTorch script gets: cuDNN's algorithm search (input is already
+            # NHWC storage viewed as NCHW, i.e. channels_last activations), bf16 autocast, CUDA graphs
+            torch.backends.cudnn.benchmark = True
         if self.backend == "tcgen05":
             from ..ops.conv_engine import MedCNNEngine
 

@@ -24,6 +24,16 @@ from .. import _ext
 from ..config import SEC_MAX_LOGQ
 
 
+import dataclasses
+
+
+@dataclasses.dataclass
+class BFVRelinKey:
+    keys: torch.Tensor        # [digits, 2, 1, N], NTT form
+    bit_count: int
+    size: int
+
+
 class BFVFracContext:
     def __init__(self, p: int = 65537, m: int = 2048, sec: int = 128, base: int = 2,
                  int_digits: int = 64, frac_digits: int = 32, device: str | torch.device = "cpu",
@@ -123,6 +133,113 @@ class BFVFracContext:
         pt = self._plain_ntt(torch.tensor([value], dtype=torch.float64), False)   # [1,N]
         out = torch.empty_like(a)
         self.ops.pointwise_(out, a.contiguous(), pt, 1, self.consts, 2)
+        return out
+
+    # ---- relinearisation keys and ciphertext x ciphertext (FLPyfhelin.py:357-364 gen_rekey) -------------
+    def relin_keygen(self, sk: torch.Tensor, seed: int, bit_count: int = 16, size: int = 1) -> "BFVRelinKey":
+        """SEAL-2.x ``relinKeyGen(bitCount, size)``: evaluation keys for s^2 -> s with decomposition base
+        w = 2^bitCount:  evk[k] = (-(a_k s + e_k) + w^k s^2, a_k), k < ceil(log2 q / bitCount), NTT form.
+        ``size`` (how many powers of s SEAL 2.x could relinearise; 5 in the reference) is recorded: products here
+        are relinearised immediately, so only the s^2 key is ever needed."""
+        bit_count = max(1, min(int(bit_count), 60))
+        t, c = self._cpu["tables"], self._cpu["consts"]
+        sk_c = sk.cpu().contiguous()
+        s2 = torch.empty_like(sk_c)
+        self.ops.pointwise_(s2, sk_c, sk_c, 1, c, 2)
+        nd = (self.q.bit_length() + bit_count - 1) // bit_count
+        keys = []
+        for k in range(nd):
+            ek = self.ops.keygen_public(sk_c, 1, self.logn, t, c, int(seed), 1 + k)        # [2,1,N]
+            term = torch.empty_like(s2)
+            self.ops.pointwise_(term, s2, torch.tensor([pow(2, k * bit_count, self.q)], dtype=torch.int64), 1, c, 5)
+            self.ops.pointwise_(ek[0], ek[0], term, 1, c, 0)
+            keys.append(ek)
+        return BFVRelinKey(torch.stack(keys).to(self.device).contiguous(), bit_count, int(size))
+
+    def _ext_basis(self):
+        """Auxiliary RNS basis {q, p1, p2, p3}: wide enough (q * 2^174) to hold the integer tensor product of two
+        ciphertexts, whose coefficients reach N * (q/2)^2, exactly."""
+        if getattr(self, "_ext", None) is None:
+            aux = []
+            for _ in range(3):
+                aux.append(int(self.ops.gen_primes(58, self.logn, 1, [self.q] + aux)[0]))
+            primes = [self.q] + aux
+            tables, consts = self.ops.build_tables(torch.tensor(primes, dtype=torch.int64), self.logn)
+            self._ext = dict(primes=primes, tables=tables, consts=consts, dev={})
+        e = self._ext
+        key = str(self.device)
+        if key not in e["dev"]:
+            e["dev"][key] = (e["tables"].to(self.device), e["consts"].to(self.device))
+        return e["primes"], e["dev"][key][0], e["dev"][key][1]
+
+    def multiply(self, a: torch.Tensor, b: torch.Tensor, rlk: "BFVRelinKey") -> torch.Tensor:
+        """BFV ciphertext product with scale-and-round and relinearisation (``PyCtxt * PyCtxt``):
+
+        1. both ciphertexts to coefficient form, centred, and into the wide basis {q, p1, p2, p3};
+        2. tensor product (d0, d1, d2) under every prime of that basis (NTT, point-wise, INTT) -- exact over Z;
+        3. CRT-compose each coefficient, y = round(p * x / q) mod q  (host big integers: this is the API-parity
+           path of dead code in the reference, not a throughput path);
+        4. relinearise d2 with the base-2^bitCount evaluation keys (fused key-switch kernel on CUDA)."""
+        import numpy as np
+
+        primes, xt, xc = self._ext_basis()
+        K = len(primes)
+        C = a.shape[0]
+        dev = self.device
+
+        def lift(ct):
+            x = ct.reshape(C * 2, self.n).clone().contiguous()
+            self.ops.ntt_(x, self.tables, self.consts, 1, self.logn, True)                 # coefficients in [0, q)
+            signed = torch.where(x > self.q // 2, x - self.q, x)                           # centred
+            limbs = torch.stack([torch.remainder(signed, p) for p in primes], dim=1).contiguous()   # [2C, K, N]
+            self.ops.ntt_(limbs, xt, xc, K, self.logn, False)
+            return limbs.view(C, 2, K, self.n)
+
+        A, B = lift(a.to(dev)), lift(b.to(dev))
+        prods = []
+        for (i, j, acc) in ((0, 0, None), (0, 1, None), (1, 0, 1), (1, 1, None)):
+            t = torch.empty(C, K, self.n, dtype=torch.int64, device=dev)
+            if acc is None:
+                self.ops.pointwise_(t, A[:, i].contiguous(), B[:, j].contiguous(), K, xc, 2)
+                prods.append(t)
+            else:
+                self.ops.pointwise_(prods[acc], A[:, i].contiguous(), B[:, j].contiguous(), K, xc, 3)   # d1 += a1*b0
+        d = torch.stack(prods, dim=1).contiguous()                                        # [C, 3, K, N]
+        self.ops.ntt_(d, xt, xc, K, self.logn, True)
+        # exact CRT -> scale-and-round, coefficient by coefficient (Python integers)
+        Q = 1
+        for p in primes:
+            Q *= p
+        res = d.cpu().numpy().astype(object)                                              # [C,3,K,N]
+        x = np.zeros(res.shape[:2] + (self.n,), dtype=object)
+        for k, p in enumerate(primes):
+            Qk = Q // p
+            x = x + res[:, :, k, :] * ((Qk * pow(Qk, -1, p)) % Q)
+        x = x % Q
+        x = np.where(x > Q // 2, x - Q, x)
+        y = (2 * self.p * x + self.q) // (2 * self.q)                                     # round(p x / q), exact
+        y = (y % self.q).astype(np.int64)
+        dq = torch.from_numpy(y).to(dev)                                                  # [C,3,N] coefficient form mod q
+        out = torch.empty(C, 2, 1, self.n, dtype=torch.int64, device=dev)
+        d01 = dq[:, :2].reshape(C * 2, self.n).clone().contiguous()
+        self.ops.ntt_(d01, self.tables, self.consts, 1, self.logn, False)
+        out[:, :, 0] = d01.view(C, 2, self.n)
+        coef2 = dq[:, 2].reshape(C, 1, self.n).contiguous()
+        evk = rlk.keys.to(dev)
+        nd = evk.shape[0]
+        done = False
+        if out.is_cuda:
+            done = self.ops.keyswitch_fused_(out, coef2, evk, [nd], [0], rlk.bit_count, self.tables, self.consts, self.logn)
+        if not done:
+            r0 = out[:, 0, 0].contiguous()
+            r1 = out[:, 1, 0].contiguous()
+            src = coef2.view(C, self.n)
+            for k in range(nd):
+                dig = self.ops.digit_extract(src, k * rlk.bit_count, rlk.bit_count)
+                self.ops.ntt_(dig, self.tables, self.consts, 1, self.logn, False)
+                self.ops.pointwise_(r0, dig, evk[k, 0, 0].contiguous(), 1, self.consts, 3)
+                self.ops.pointwise_(r1, dig, evk[k, 1, 0].contiguous(), 1, self.consts, 3)
+            out[:, 0, 0], out[:, 1, 0] = r0, r1
         return out
 
     def noise_budget_bits(self, ct: torch.Tensor, sk: torch.Tensor) -> float:

@@ -173,6 +173,18 @@ class CKKSContext:
             keys.append(torch.stack(row).to(self.device))
         return RelinKey(keys, digit_bits)
 
+    @staticmethod
+    def _flat_evk(rlk: "RelinKey"):
+        """[E, 2, L, N] evaluation keys + per-source-limb (digit count, first entry) for the fused key switch."""
+        if getattr(rlk, "_flat", None) is None:
+            nd = [int(k.shape[0]) for k in rlk.keys]
+            first, acc = [], 0
+            for d in nd:
+                first.append(acc)
+                acc += d
+            rlk._flat = (torch.cat(list(rlk.keys), dim=0).contiguous(), nd, first)
+        return rlk._flat
+
     # ------------------------------------------------------------------ encode / encrypt
     def encode(self, vals: torch.Tensor, packing: str = "slots", scale: Optional[float] = None,
                count: Optional[int] = None) -> torch.Tensor:
@@ -303,6 +315,15 @@ class CKKSContext:
             raise ValueError("no limb left to drop")
         C = a.count
         ql = self.primes[lvl - 1]
+        if a.data.is_cuda:
+            # one fused launch (csrc/he/cuda/he_eval2.cu): INTT of the last limb -> centred lift -> NTT under every
+            # remaining prime -> subtract -> * q_last^-1
+            out = self.ops.rescale_fused(a.data.contiguous(), self.tables, self.consts, self.consts_cpu, self.logn)
+            if out.numel() or C == 0:
+                a.data = out if out.numel() else a.data[:, :, :lvl - 1].contiguous()
+                a.scale = a.scale / float(ql)
+                return a
+        # reference path (CPU tensors, N >= 16384, primes >= 2^58): the same steps, limb by limb
         # last limb to coefficient form
         last = a.data[:, :, lvl - 1].contiguous()            # [C,2,N]
         self._ntt_single_limb(last, lvl - 1, inverse=True)
@@ -328,6 +349,17 @@ class CKKSContext:
         """ct * ct with relinearisation (API parity: PyCtxt * PyCtxt)."""
         self._check_compatible(a, b, same_scale=False)
         lvl = a.level
+        if a.data.is_cuda and lvl == self.L and rlk is not None:
+            # fused path: one tensor-product kernel, one batched INTT, one key-switch kernel that accumulates
+            # every (source limb, digit) term in shared memory on top of (d0, d1)
+            d01, d2 = self.ops.ct_tensor(a.data.contiguous(), b.data.contiguous(), self.consts)
+            self.ops.ntt_(d2, self.tables, self.consts, lvl, self.logn, True)
+            evk, nd, first = self._flat_evk(rlk)
+            if self.ops.keyswitch_fused_(d01, d2, evk, nd, first, rlk.digit_bits, self.tables, self.consts, self.logn):
+                out = CtBatch(d01, a.scale * b.scale, min(a.nvals, b.nvals), a.packing)
+                if rescale:
+                    self.rescale_(out)
+                return out
         a0, a1 = a.data[:, 0].contiguous(), a.data[:, 1].contiguous()
         b0, b1 = b.data[:, 0].contiguous(), b.data[:, 1].contiguous()
         d0 = torch.empty_like(a0)

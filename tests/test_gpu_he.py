@@ -191,3 +191,31 @@ def test_pipelined_fedavg_matches_unchunked():
     agg = run.aggregate(ct)
     run.decrypt_apply(agg)
     assert (run.pack.flat - w).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("n,bits", [(2048, (54, 50)), (4096, (36, 36, 37)), (8192, (54, 54, 54, 55))])
+def test_fused_rescale_and_keyswitch_match_the_reference_loops(n, bits):
+    """The one-launch rescale and key-switch kernels (he_eval2.cu) against the limb-by-limb reference path that
+    runs on the host twin: exact modular arithmetic, so the ciphertexts must be identical word for word."""
+    from hefl_b200.he.context import CtBatch, RelinKey
+
+    c, g = _ctx_pair(n, bits)
+    sk, pk = c.keygen(seed=3)
+    rlk_c = c.relin_keygen(sk, seed=4, digit_bits=14)
+    rlk_g = RelinKey([k.cuda() for k in rlk_c.keys], rlk_c.digit_bits)
+    gen = torch.Generator().manual_seed(5)
+    nv = 3 * (n // 2) - 7                                  # three ciphertexts: a partial unit for n < 8192
+    va, vb = torch.rand(nv, generator=gen) * 2 - 1, torch.rand(nv, generator=gen) + 0.5
+    ca, cb = c.encrypt(va, pk, seed=1), c.encrypt(vb, pk, seed=2)
+    ga = CtBatch(ca.data.cuda(), ca.scale, ca.nvals, ca.packing)
+    gb = CtBatch(cb.data.cuda(), cb.scale, cb.nvals, cb.packing)
+    # rescale alone (after a scalar multiply) ...
+    r_c = c.mul_scalar_(ca.clone(), 0.375)
+    r_g = g.mul_scalar_(ga.clone(), 0.375)
+    assert r_g.level == len(bits) - 1 and torch.equal(r_g.data.cpu(), r_c.data)
+    # ... and the whole ct x ct path: tensor product, key switch, rescale
+    p_c = c.multiply(ca, cb, rlk_c, rescale=True)
+    p_g = g.multiply(ga, gb, rlk_g, rescale=True)
+    assert torch.equal(p_g.data.cpu(), p_c.data)
+    out = g.decrypt(p_g, sk.cuda())
+    assert (out.cpu() - va * vb).abs().max() < 5e-3

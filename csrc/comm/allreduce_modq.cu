@@ -117,10 +117,12 @@ __device__ __forceinline__ uint64_t mod_sum(uint64_t s, uint64_t q, uint64_t rat
 
 // Work is cut into "quads" of 4 words (32 bytes). A quad never straddles a limb (N >= 1024),
 // so q is fetched once per quad.
-constexpr int kUnroll = 1;      // quads per thread per step in the P2P algorithms: P * 32 B in flight per thread (2 spill)
+// Quads per thread per step in the P2P algorithms: U * P * 32 bytes in flight per thread. What matters is the
+// number of REMOTE loads in flight per SM (peer latency is ~2.5 us): with two ranks a thread has one remote
+// load per quad, with eight it has seven, so U shrinks as the world grows (and the registers stay <= 64 words).
 constexpr int kMmUnroll = 2;    // quads per thread per step for multimem: 8 independent ld_reduce in flight
 
-template <int ALGO>  // 0 two_shot, 1 one_shot, 2 multimem
+template <int ALGO, int kUnroll>  // ALGO: 0 two_shot, 1 one_shot, 2 multimem
 __global__ void __launch_bounds__(512)
 allreduce_modq_kernel(const __grid_constant__ AllReduceArgs a) {
   const uint64_t deadline = globaltimer_ns() + a.timeout_ns;
@@ -175,13 +177,14 @@ allreduce_modq_kernel(const __grid_constant__ AllReduceArgs a) {
     }
   } else {
     for (int64_t i0 = lo + tid; i0 < hi; i0 += nthreads * kUnroll) {
-      U64x4 v[kUnroll][kMaxWorld];
+      constexpr int kPeers = kMaxWorld / kUnroll;       // this instantiation serves worlds up to kPeers
+      U64x4 v[kUnroll][kPeers];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         const int64_t i = i0 + u * nthreads;
         if (i < hi) {
 #pragma unroll
-          for (int p = 0; p < kMaxWorld; ++p)
+          for (int p = 0; p < kPeers; ++p)
             if (p < P) v[u][p] = ld32(a.bufs[(a.rank + p) % P] + (i << 2));  // stagger peers across ranks
           ++peer_loads;
         }
@@ -194,7 +197,7 @@ allreduce_modq_kernel(const __grid_constant__ AllReduceArgs a) {
           const uint64_t q = a.q[l], rh = a.ratio_hi[l];
           U64x4 acc = v[u][0];
 #pragma unroll
-          for (int p = 1; p < kMaxWorld; ++p)
+          for (int p = 1; p < kPeers; ++p)
             if (p < P) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) acc.v[k] += v[u][p].v[k];
@@ -218,8 +221,8 @@ allreduce_modq_kernel(const __grid_constant__ AllReduceArgs a) {
   block_barrier(a, 1, deadline);
 }
 
-template <int ALGO>
-static void launch_allreduce(const AllReduceArgs& args, int blocks, int threads, cudaStream_t st) {
+template <int ALGO, int U>
+static void launch_allreduce_u(const AllReduceArgs& args, int blocks, int threads, cudaStream_t st) {
   // Even grids go out as clusters of two CTAs: a cluster takes both SMs of a TPC, so a small grid (the
   // SM-partitioned pipeline gives the collective ~24 SMs) does not leave half-used TPCs that the cluster
   // kernels of encrypt / decrypt could no longer be placed on.
@@ -234,7 +237,14 @@ static void launch_allreduce(const AllReduceArgs& args, int blocks, int threads,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, allreduce_modq_kernel<ALGO>, args);
+  cudaLaunchKernelEx(&cfg, allreduce_modq_kernel<ALGO, U>, args);
+}
+
+template <int ALGO>
+static void launch_allreduce(const AllReduceArgs& args, int blocks, int threads, cudaStream_t st) {
+  if (ALGO == 2 || args.world > 4) launch_allreduce_u<ALGO, 1>(args, blocks, threads, st);
+  else if (args.world > 2) launch_allreduce_u<ALGO, 2>(args, blocks, threads, st);
+  else launch_allreduce_u<ALGO, 4>(args, blocks, threads, st);
 }
 
 void allreduce_modq(const AllReduceArgs& args, int algo, int blocks, int threads, cudaStream_t st) {

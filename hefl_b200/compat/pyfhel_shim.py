@@ -21,11 +21,13 @@ from __future__ import annotations
 import struct
 from typing import Optional, Sequence, Union
 
+import os
 import secrets
 
 import numpy as np
 import torch
 
+from . import seal_format
 from ..he.bfv import BFVFracContext
 from ..he.context import CKKSContext, CtBatch
 
@@ -195,12 +197,45 @@ class Pyfhel:
         raise NotImplementedError("rotations are not used by the reference (repr shows rtk:-)")
 
     # ------------------------------------------------------------------ (de)serialization
-    def to_bytes_context(self) -> bytes:
+    def _fmt(self, format: Optional[str]) -> str:
+        f = (format or os.environ.get("HEFL_SERIALIZATION", "native")).lower()
+        if f not in ("native", "seal2"):
+            raise ValueError(f"unknown serialization format {f!r}")
+        if f == "seal2" and self._scheme != ENC_FRACTIONAL:
+            raise NotImplementedError("the SEAL-2.3 layout exists for the BFV/fractional scheme of the reference")
+        return f
+
+    def _seal_hash(self) -> bytes:
+        c = self._ctx
+        return seal_format.params_hash(c.n, [c.q], c.p)
+
+    def _to_coeff(self, t: torch.Tensor, inverse: bool) -> torch.Tensor:
+        """[..., 1, N] between NTT form (ours) and coefficient form (the seal2 streams)."""
+        x = t.detach().to(self._device).reshape(-1, self._ctx.n).clone().contiguous()
+        self._ctx.ops.ntt_(x, self._ctx.tables, self._ctx.consts, 1, self._ctx.logn, inverse)
+        return x.reshape(t.shape)
+
+    def to_bytes_context(self, format: Optional[str] = None) -> bytes:
+        """``format="seal2"`` (or HEFL_SERIALIZATION=seal2): SEAL-2.3 EncryptionParameters layout followed by the
+        encoder settings Afseal keeps next to them (compat/seal_format.py); default: our versioned stream."""
         self._need_ctx()
+        if self._fmt(format) == "seal2":
+            c = self._ctx
+            return seal_format.context_to_bytes(c.n, [c.q], c.p, c.base, c.sec, c.int_digits, c.frac_digits, False)
         tag = b"C" if self._scheme == ENC_CKKS else b"F"
         return tag + self._ctx.to_bytes_context()
 
     def from_bytes_context(self, buf: bytes) -> None:
+        if buf[:1] not in (b"C", b"F"):
+            # SEAL-2.3 layout: starts with BigPoly(x^N + 1) = int32 coeff_count (N + 1), int32 bit count (1)
+            d = seal_format.context_from_bytes(buf)
+            if len(d["coeff_moduli"]) != 1:
+                raise NotImplementedError("seal2 contexts with several coefficient moduli")
+            self._ctx = BFVFracContext(p=d["plain_modulus"], m=d["n"], sec=d["sec"], base=d["base"],
+                                       int_digits=d["int_digits"], frac_digits=d["frac_digits"], device=self._device,
+                                       q=d["coeff_moduli"][0])
+            self._scheme = ENC_FRACTIONAL
+            return
         if buf[:1] == b"C":
             self._ctx = CKKSContext.from_bytes_context(buf[1:], device=self._device)
             self._scheme = ENC_CKKS
@@ -223,23 +258,53 @@ class Pyfhel:
         arr = np.frombuffer(buf, dtype=np.int64, offset=5 + 8 * nd).reshape(shape).copy()
         return torch.from_numpy(arr).to(self._device)
 
-    def to_bytes_publicKey(self) -> bytes:
+    def to_bytes_publicKey(self, format: Optional[str] = None) -> bytes:
         if self._pk is None:
             raise RuntimeError("no public key")
+        if self._fmt(format) == "seal2":
+            return seal_format.polys_to_bytes(self._seal_hash(), self._to_coeff(self._pk, True).cpu().numpy())
         return self._key_bytes(self._pk, b"P")
 
-    def to_bytes_secretKey(self) -> bytes:
+    def to_bytes_secretKey(self, format: Optional[str] = None) -> bytes:
         if self._sk is None:
             raise RuntimeError("no secret key")
+        if self._fmt(format) == "seal2":
+            return seal_format.secret_to_bytes(self._seal_hash(), self._to_coeff(self._sk, True).cpu().numpy())
         return self._key_bytes(self._sk, b"S")
+
+    def _is_seal(self, buf: bytes) -> bool:
+        return self._scheme == ENC_FRACTIONAL and bytes(buf[:32]) == self._seal_hash()
 
     def from_bytes_publicKey(self, buf: bytes) -> None:
         self._need_ctx()
+        if self._is_seal(buf):
+            _, polys, _ = seal_format.polys_from_bytes(buf)
+            self._pk = self._to_coeff(torch.from_numpy(polys), False)
+            return
         self._pk = self._key_from(buf, b"P")
 
     def from_bytes_secretKey(self, buf: bytes) -> None:
         self._need_ctx()
+        if self._is_seal(buf):
+            _, poly, _ = seal_format.secret_from_bytes(buf)
+            self._sk = self._to_coeff(torch.from_numpy(poly), False)
+            return
         self._sk = self._key_from(buf, b"S")
+
+    def ctxt_to_bytes(self, ct: "PyCtxt", format: Optional[str] = None) -> bytes:
+        """One fractional ciphertext as a SEAL-2.3 Ciphertext stream (hash block, size, N + 1, modulus count,
+        coefficient-form words) or our raw words."""
+        if self._fmt(format) == "seal2":
+            return seal_format.polys_to_bytes(self._seal_hash(), self._to_coeff(ct._data, True).cpu().numpy())
+        return ct.to_bytes()
+
+    def ctxt_from_bytes(self, buf: bytes) -> "PyCtxt":
+        if self._is_seal(buf):
+            hb, polys, _ = seal_format.polys_from_bytes(buf)
+            return PyCtxt(self, self._to_coeff(torch.from_numpy(polys), False), ENC_FRACTIONAL)
+        n = self._ctx.n
+        arr = np.frombuffer(buf, dtype=np.int64).reshape(2, -1, n).copy()
+        return PyCtxt(self, torch.from_numpy(arr).to(self._device), self._scheme)
 
     # aliases used by other Pyfhel versions
     to_bytes_public_key, to_bytes_secret_key = to_bytes_publicKey, to_bytes_secretKey

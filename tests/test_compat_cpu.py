@@ -130,3 +130,19 @@ def test_notebook_cell3_sequence_end_to_end(tmp_path, monkeypatch):
         os.chdir(cwd)
     for a, x, y in zip(agg, w1, w2):
         assert np.allclose(a, (x + y) / 2, atol=1e-6)
+
+
+def test_a_real_keras_hdf5_file_is_recognised_and_reported(tmp_path):
+    """Files that carry the HDF5 signature go to the h5py reader; without h5py the error says what is missing
+    instead of failing inside torch.load."""
+    import importlib.util
+
+    import pytest
+
+    from hefl_b200.compat import keras_like
+
+    p = tmp_path / "main_model.hdf5"
+    p.write_bytes(keras_like.HDF5_MAGIC + b"\x00" * 64)
+    if importlib.util.find_spec("h5py") is None:
+        with pytest.raises(RuntimeError, match="h5py"):
+            keras_like.load_model(str(p))

@@ -132,7 +132,7 @@ def main():
             try:
                 from hefl_b200.ops import conv_engine  # noqa: F401
 
-                nn_backend = "tcgen05" if args.model == "medcnn" else "cudnn"
+                nn_backend = "tcgen05"       # medcnn: the fused engine; ResNets: tcgen05 GEMM convolutions
             except Exception:  # noqa: BLE001
                 nn_backend = "cudnn"
         transport = "nccl" if impl == "baseline" else (args.transport or "fused")

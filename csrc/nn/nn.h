@@ -38,6 +38,15 @@ void head_cluster(const void* feat, const float* W1, const float* b1, const floa
 bool wgrad0_gather_supported(int W, int Wp, int CK, int Ci, int Co);
 void wgrad0_gather(const void* X, const void* g, const uint8_t* amax, float* dW, int B, int H, int W, int Hp, int Wp,
                    cudaStream_t st);
+// ---- general tcgen05 GEMMs for the ResNet convolutions (gemm_tcgen05.cu) ----
+// C[rows_out, N] (bf16) = sum_{t < taps} A[m + shifts[t], K] . B[t*N + n, K]^T. padded != 0: A rows index a zero-padded
+// [Bn][H+2][W+2] grid and only interior pixels are written (to the dense [Bn*H*W, N] output). fp8: A and B hold e4m3
+// bytes and the product of the two device scalars scale_a * scale_b multiplies the result.
+void gemm_taps(const void* A, const void* Bm, void* C, int64_t a_rows, int N, int K, int taps, const int* shifts, int padded,
+               int Bn, int H, int W, bool fp8, const float* scale_a, const float* scale_b, cudaStream_t st);
+// dW[taps][Co][Ci] (fp32, zeroed by the caller) += dY[rows, Co]^T . X[rows + shift(tap), Ci]; taps = 1, or 9 on a padded
+// grid whose rows are Wp pixels long.
+void wgrad_taps(const void* DY, const void* X, float* dW, int64_t rows, int Co, int Ci, int taps, int Wp, cudaStream_t st);
 // ---- ResNet building blocks (resnet_kernels.cu) ----
 void bn_forward(const void* x, const void* res, const float* gamma, const float* beta, float* run_mean, float* run_var,
                 float* mean, float* invstd, float* sums, void* y, int64_t P, int C, float momentum, float eps, int relu,

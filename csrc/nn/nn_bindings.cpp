@@ -259,6 +259,38 @@ void avgpool_backward(const Tensor& dout, Tensor dx, int64_t B, int64_t HW, int6
 }
 
 // q = e4m3(sat(x * scale)) (q: uint8 storage, viewed as float8_e4m3fn by the caller); amax = max(amax, |x|).
+// out[rows_out, N] bf16 = sum_taps A[m + shift, K] . B[t*N + n, K]^T (tcgen05; csrc/nn/gemm_tcgen05.cu)
+void gemm_taps(const Tensor& A, const Tensor& Bm, Tensor out, int64_t N, int64_t K, at::IntArrayRef shifts, int64_t padded,
+               int64_t Bn, int64_t H, int64_t W, const c10::optional<Tensor>& scale_a, const c10::optional<Tensor>& scale_b) {
+  TORCH_CHECK(A.is_cuda() && Bm.is_cuda() && out.is_cuda(), "gemm_taps is a CUDA (sm_100a) op");
+  TORCH_CHECK(A.is_contiguous() && Bm.is_contiguous() && out.is_contiguous(), "contiguous operands expected");
+  const bool fp8 = A.element_size() == 1;
+  TORCH_CHECK(A.element_size() == Bm.element_size() && (fp8 || A.scalar_type() == at::kBFloat16), "bf16 or e4m3 operands");
+  TORCH_CHECK(out.scalar_type() == at::kBFloat16, "bf16 output");
+  const int taps = shifts.empty() ? 1 : (int)shifts.size();
+  const int64_t a_rows = A.numel() / K;
+  TORCH_CHECK(Bm.numel() == (int64_t)taps * N * K, "B must be [taps*N, K]");
+  const int64_t rows_out = padded ? Bn * H * W : a_rows;
+  TORCH_CHECK(out.numel() == rows_out * N, "output must be [rows_out, N]");
+  if (padded) TORCH_CHECK(a_rows == Bn * (H + 2) * (W + 2), "A must cover the padded grid");
+  std::vector<int> sh(shifts.begin(), shifts.end());
+  hefl::nn::gemm_taps(A.data_ptr(), Bm.data_ptr(), out.data_ptr(), a_rows, (int)N, (int)K, taps, sh.empty() ? nullptr : sh.data(),
+                      (int)padded, (int)Bn, (int)H, (int)W, fp8, scale_a.has_value() ? scale_a->data_ptr<float>() : nullptr,
+                      scale_b.has_value() ? scale_b->data_ptr<float>() : nullptr, cur());
+}
+
+// dW [taps, Co, Ci] fp32 (zeroed here) = dY[rows, Co]^T . X[rows + shift(tap), Ci]
+void wgrad_taps(const Tensor& DY, const Tensor& X, Tensor dW, int64_t taps, int64_t Wp) {
+  TORCH_CHECK(DY.is_cuda() && X.is_cuda() && dW.is_cuda(), "wgrad_taps is a CUDA (sm_100a) op");
+  TORCH_CHECK(DY.scalar_type() == at::kBFloat16 && X.scalar_type() == at::kBFloat16 && dW.scalar_type() == at::kFloat, "dtypes");
+  TORCH_CHECK(DY.dim() == 2 && X.dim() == 2 && DY.size(0) == X.size(0) && DY.is_contiguous() && X.is_contiguous() && dW.is_contiguous(),
+              "DY [rows, Co], X [rows, Ci]");
+  const int64_t Co = DY.size(1), Ci = X.size(1);
+  TORCH_CHECK(dW.numel() == taps * Co * Ci, "dW must be [taps, Co, Ci]");
+  dW.zero_();
+  hefl::nn::wgrad_taps(DY.data_ptr(), X.data_ptr(), dW.data_ptr<float>(), DY.size(0), (int)Co, (int)Ci, (int)taps, (int)Wp, cur());
+}
+
 void fp8_quantize(const Tensor& x, Tensor q, const Tensor& scale, Tensor amax) {
   chk_bf16(x, "x");
   TORCH_CHECK(q.is_cuda() && q.is_contiguous() && q.element_size() == 1 && q.numel() == x.numel(), "q must be a 1-byte tensor like x");
@@ -340,6 +372,8 @@ TORCH_LIBRARY_FRAGMENT(hefl, m) {
   m.def("set_pdl(int on) -> ()", [](int64_t on) { hefl::nn::set_pdl((int)on); });
   m.def("wgrad0_gather(Tensor X, Tensor g, Tensor amax, Tensor(a!) dW32, int B, int H, int W) -> ()", &wgrad0_gather);
   m.def("fp8_quantize(Tensor x, Tensor(a!) q, Tensor scale, Tensor(b!) amax) -> ()", &fp8_quantize);
+  m.def("gemm_taps(Tensor A, Tensor B, Tensor(a!) out, int N, int K, int[] shifts, int padded, int Bn, int H, int W, Tensor? scale_a, Tensor? scale_b) -> ()", &gemm_taps);
+  m.def("wgrad_taps(Tensor DY, Tensor X, Tensor(a!) dW, int taps, int Wp) -> ()", &wgrad_taps);
   m.def("bn_forward(Tensor x, Tensor? res, Tensor gamma, Tensor beta, Tensor(a!)? run_mean, Tensor(b!)? run_var, Tensor(c!) mean, Tensor(d!) invstd, Tensor(e!) sums, Tensor(f!) y, float momentum, float eps, bool relu) -> ()", &bn_forward);
   m.def("bn_backward(Tensor dy, Tensor x, Tensor y, Tensor mean, Tensor invstd, Tensor gamma, Tensor(a!) sums, Tensor(b!) dx, Tensor(c!)? dres, bool relu) -> ()", &bn_backward);
   m.def("avgpool_forward(Tensor x, Tensor(a!) out, int B, int HW, int C) -> ()", &avgpool_forward);

@@ -42,6 +42,7 @@ CUDA_SOURCES = [
     "he/cuda/he_eval2.cu",
     "comm/allreduce_modq.cu",
     "nn/conv_tcgen05.cu",
+    "nn/gemm_tcgen05.cu",
     "nn/nn_kernels.cu",
     "nn/resnet_kernels.cu",
     "nn/wgrad_gather.cu",

@@ -79,6 +79,14 @@ class LocalTrainer:
             # the library arm gets what a tuned PyTorch script gets: cuDNN's algorithm search (input is already
             # NHWC storage viewed as NCHW, i.e. channels_last activations), bf16 autocast, CUDA graphs
             torch.backends.cudnn.benchmark = True
+        if self.backend == "tcgen05" and not hasattr(model, "convs"):
+            # the ResNets: same autograd / CUDA-graph step as the library arm, with every eligible convolution
+            # (1x1, 3x3 stride 1) on the tcgen05 GEMM kernels of ops/tc_conv.py
+            from ..ops import tc_conv
+
+            tc_conv.set_model_tc(model, self.cuda)
+            torch.backends.cudnn.benchmark = True        # the stem and the three stride-2 3x3 layers stay on cuDNN
+            self.backend = "tcgen05-gemm"
         if self.backend == "tcgen05":
             from ..ops.conv_engine import MedCNNEngine
 

@@ -11,6 +11,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..ops.fp8 import Conv1x1
+from ..ops.tc_conv import Conv3x3
 from ..ops.resnet_ops import bn_act, global_avgpool
 
 
@@ -19,9 +20,9 @@ class BasicBlock(nn.Module):
 
     def __init__(self, cin: int, planes: int, stride: int = 1):
         super().__init__()
-        self.conv1 = nn.Conv2d(cin, planes, 3, stride, 1, bias=False)
+        self.conv1 = Conv3x3(cin, planes, stride)
         self.bn1 = nn.BatchNorm2d(planes)
-        self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
+        self.conv2 = Conv3x3(planes, planes, 1)
         self.bn2 = nn.BatchNorm2d(planes)
         self.down = None
         if stride != 1 or cin != planes:
@@ -40,7 +41,7 @@ class Bottleneck(nn.Module):
         super().__init__()
         self.conv1 = Conv1x1(cin, planes)
         self.bn1 = nn.BatchNorm2d(planes)
-        self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
+        self.conv2 = Conv3x3(planes, planes, stride)
         self.bn2 = nn.BatchNorm2d(planes)
         self.conv3 = Conv1x1(planes, planes * 4)
         self.bn3 = nn.BatchNorm2d(planes * 4)

@@ -87,9 +87,19 @@ class Conv1x1(nn.Conv2d):
         super().__init__(cin, cout, 1, stride, 0, bias=False)
         self._fp8_state = None
         self.use_fp8 = None          # None: follow the module-level ENABLE; True / False: per-model choice (trainer)
+        self.use_tc = None           # hand-written tcgen05 GEMM (ops/tc_conv.py) instead of cuDNN / cuBLASLt
 
     def forward(self, x):
         on = ENABLE if self.use_fp8 is None else self.use_fp8
+        from . import tc_conv
+
+        if (tc_conv.ENABLE if self.use_tc is None else self.use_tc) and tc_conv.eligible(x, self.in_channels, self.out_channels):
+            st = None
+            if on:
+                if self._fp8_state is None:
+                    self._fp8_state = (DelayedScale(x.device), DelayedScale(x.device))
+                st = self._fp8_state
+            return tc_conv.conv1x1(x, self.weight, self.stride[0], st)
         ok = (on and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4
               and self.in_channels % 16 == 0 and self.out_channels % 16 == 0)
         if not ok:

@@ -451,7 +451,77 @@ void launch_wgrad_mn(const void* DY, const void* X, const WgArgs& a, int64_t row
   hefl::cuda::note_launch();
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// data movement around the GEMMs: one pass each (ATen needs a fill + a strided copy, resp. cast + permute + flip)
+// ------------------------------------------------------------------------------------------------------------
+// x [B][H][W][C] -> xp [B][H+2][W+2][C] with a zero border; 16-byte vectors, C % 8 == 0
+__global__ void pad_nhwc_kernel(const uint4* __restrict__ x, uint4* __restrict__ xp, int B, int H, int W, int C8) {
+  const int Hp = H + 2, Wp = W + 2;
+  const int64_t total = (int64_t)B * Hp * Wp * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    int64_t p = i / C8;
+    const int wp = (int)(p % Wp);
+    p /= Wp;
+    const int hp = (int)(p % Hp);
+    const int b = (int)(p / Hp);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (hp >= 1 && hp <= H && wp >= 1 && wp <= W) v = x[(((int64_t)b * H + hp - 1) * W + wp - 1) * C8 + c];
+    xp[i] = v;
+  }
+}
+
+// w fp32 [Co][Ci][3][3] -> wt bf16 [tap][Co][Ci] (forward) and wd bf16 [tap][Ci][Co] with the filter rotated by 180
+// degrees (dgrad); for k = 1: wt [Co][Ci] and wd = its transpose [Ci][Co]
+__global__ void conv_weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wt,
+                                        __nv_bfloat16* __restrict__ wd, int Co, int Ci, int kk) {
+  const int64_t total = (int64_t)kk * Co * Ci;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Ci);
+    const int co = (int)((i / Ci) % Co);
+    const int tap = (int)(i / ((int64_t)Ci * Co));
+    const __nv_bfloat16 v = __float2bfloat16(w[((int64_t)co * Ci + ci) * kk + tap]);
+    wt[i] = v;
+    if (wd) wd[((int64_t)(kk - 1 - tap) * Ci + ci) * Co + co] = v;
+  }
+}
+
+// dW fp32 [tap][Co][Ci] -> grad fp32 [Co][Ci][kh][kw]
+__global__ void conv_wgrad_unpack_kernel(const float* __restrict__ dw, float* __restrict__ g, int Co, int Ci, int kk) {
+  const int64_t total = (int64_t)kk * Co * Ci;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % kk);
+    const int64_t cc = i / kk;                     // co * Ci + ci
+    g[i] = dw[(int64_t)tap * Co * Ci + cc];
+  }
+}
+
 }  // namespace
+
+void pad_nhwc(const void* x, void* xp, int B, int H, int W, int C, cudaStream_t st) {
+  if (C % 8) throw std::runtime_error("pad_nhwc: C must be a multiple of 8");
+  const int64_t total = (int64_t)B * (H + 2) * (W + 2) * (C / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pad_nhwc_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(xp), B, H, W, C / 8);
+  hefl::cuda::note_launch();
+}
+
+void conv_weight_prep(const float* w, void* wt, void* wd, int Co, int Ci, int kk, cudaStream_t st) {
+  const int64_t total = (int64_t)kk * Co * Ci;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  conv_weight_prep_kernel<<<blocks, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(wt), reinterpret_cast<__nv_bfloat16*>(wd), Co, Ci, kk);
+  hefl::cuda::note_launch();
+}
+
+void conv_wgrad_unpack(const float* dw, float* g, int Co, int Ci, int kk, cudaStream_t st) {
+  const int64_t total = (int64_t)kk * Co * Ci;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  conv_wgrad_unpack_kernel<<<blocks, 256, 0, st>>>(dw, g, Co, Ci, kk);
+  hefl::cuda::note_launch();
+}
 
 // C[rows_out, N] (bf16) = sum_taps A[m + shift_t, K] . B[t*N + n, K]; see GemmArgs. fp8: A, B are e4m3 bytes.
 void gemm_taps(const void* A, const void* Bm, void* C, int64_t a_rows, int N, int K, int taps, const int* shifts, int padded,
@@ -498,7 +568,8 @@ void wgrad_taps(const void* DY, const void* X, float* dW, int64_t rows, int Co, 
   for (int g = 0; g < a.groups; ++g) a.gshift[g] = taps == 9 ? (g - 1) * Wp - 1 : 0;
   a.kchunks = (int)((rows + 63) / 64);
   const int base_units = a.co_tiles * a.ci_tiles * a.groups;
-  int ks = (2 * sm_count() + base_units - 1) / base_units;
+  int ks = (sm_count() + base_units - 1) / base_units;          // about one wave of CTAs: longer K runs per unit,
+                                                                // fewer REDs onto the same dW words
   if (ks < 1) ks = 1;
   if (ks > a.kchunks) ks = a.kchunks;
   a.ksplit = ks;

@@ -47,6 +47,9 @@ void gemm_taps(const void* A, const void* Bm, void* C, int64_t a_rows, int N, in
 // dW[taps][Co][Ci] (fp32, zeroed by the caller) += dY[rows, Co]^T . X[rows + shift(tap), Ci]; taps = 1, or 9 on a padded
 // grid whose rows are Wp pixels long.
 void wgrad_taps(const void* DY, const void* X, float* dW, int64_t rows, int Co, int Ci, int taps, int Wp, cudaStream_t st);
+void pad_nhwc(const void* x, void* xp, int B, int H, int W, int C, cudaStream_t st);          // bf16, zero border of 1
+void conv_weight_prep(const float* w, void* wt, void* wd, int Co, int Ci, int kk, cudaStream_t st);
+void conv_wgrad_unpack(const float* dw, float* g, int Co, int Ci, int kk, cudaStream_t st);
 // ---- ResNet building blocks (resnet_kernels.cu) ----
 void bn_forward(const void* x, const void* res, const float* gamma, const float* beta, float* run_mean, float* run_var,
                 float* mean, float* invstd, float* sums, void* y, int64_t P, int C, float momentum, float eps, int relu,
@@ -56,6 +59,7 @@ void bn_backward(const void* dy, const void* x, const void* y, const float* mean
 void avgpool_forward(const void* x, float* out, int B, int HW, int C, cudaStream_t st);
 void avgpool_backward(const float* dout, void* dx, int B, int HW, int C, cudaStream_t st);
 void fp8_quantize(const void* x, uint8_t* q, const float* scale, float* amax, int64_t n, cudaStream_t st);
+void fp8_scale_update(float* amax, float* scale, float* inv, float target, cudaStream_t st);
 void umma_shift_probe(const void* A, const void* Bm, float* out, int CK, int shift_rows, int mode, cudaStream_t st);
 
 // ---- data-movement kernels around the convolutions (nn_kernels.cu) ----

@@ -291,6 +291,39 @@ void wgrad_taps(const Tensor& DY, const Tensor& X, Tensor dW, int64_t taps, int6
   hefl::nn::wgrad_taps(DY.data_ptr(), X.data_ptr(), dW.data_ptr<float>(), DY.size(0), (int)Co, (int)Ci, (int)taps, (int)Wp, cur());
 }
 
+void fp8_scale_update(Tensor amax, Tensor scale, Tensor inv, double target) {
+  TORCH_CHECK(amax.is_cuda() && amax.scalar_type() == at::kFloat && scale.scalar_type() == at::kFloat && inv.scalar_type() == at::kFloat,
+              "fp32 CUDA scalars expected");
+  hefl::nn::fp8_scale_update(amax.data_ptr<float>(), scale.data_ptr<float>(), inv.data_ptr<float>(), (float)target, cur());
+}
+
+// x: channels_last bf16 [B,C,H,W] (i.e. NHWC storage) -> zero-padded NHWC [B,H+2,W+2,C] in one pass
+Tensor pad_nhwc(const Tensor& x) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.dim() == 4 && x.is_contiguous(at::MemoryFormat::ChannelsLast),
+              "pad_nhwc expects a channels_last bf16 CUDA tensor");
+  const int64_t B = x.size(0), C = x.size(1), H = x.size(2), W = x.size(3);
+  Tensor xp = at::empty({B, H + 2, W + 2, C}, x.options());
+  hefl::nn::pad_nhwc(x.data_ptr(), xp.data_ptr(), (int)B, (int)H, (int)W, (int)C, cur());
+  return xp;
+}
+
+// fp32 [Co,Ci,k,k] -> (bf16 [k*k*Co, Ci] forward taps, bf16 [k*k*Ci, Co] rotated / transposed taps for dgrad)
+std::tuple<Tensor, Tensor> conv_weight_prep(const Tensor& w) {
+  TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kFloat && w.dim() == 4 && w.is_contiguous(), "fp32 [Co,Ci,k,k] weights");
+  const int64_t Co = w.size(0), Ci = w.size(1), kk = w.size(2) * w.size(3);
+  Tensor wt = at::empty({kk * Co, Ci}, w.options().dtype(at::kBFloat16));
+  Tensor wd = at::empty({kk * Ci, Co}, w.options().dtype(at::kBFloat16));
+  hefl::nn::conv_weight_prep(w.data_ptr<float>(), wt.data_ptr(), wd.data_ptr(), (int)Co, (int)Ci, (int)kk, cur());
+  return {wt, wd};
+}
+
+Tensor conv_wgrad_unpack(const Tensor& dw, int64_t Co, int64_t Ci, int64_t k) {
+  TORCH_CHECK(dw.is_cuda() && dw.scalar_type() == at::kFloat && dw.is_contiguous() && dw.numel() == k * k * Co * Ci, "dW [k*k,Co,Ci]");
+  Tensor g = at::empty({Co, Ci, k, k}, dw.options());
+  hefl::nn::conv_wgrad_unpack(dw.data_ptr<float>(), g.data_ptr<float>(), (int)Co, (int)Ci, (int)(k * k), cur());
+  return g;
+}
+
 void fp8_quantize(const Tensor& x, Tensor q, const Tensor& scale, Tensor amax) {
   chk_bf16(x, "x");
   TORCH_CHECK(q.is_cuda() && q.is_contiguous() && q.element_size() == 1 && q.numel() == x.numel(), "q must be a 1-byte tensor like x");
@@ -374,6 +407,10 @@ TORCH_LIBRARY_FRAGMENT(hefl, m) {
   m.def("fp8_quantize(Tensor x, Tensor(a!) q, Tensor scale, Tensor(b!) amax) -> ()", &fp8_quantize);
   m.def("gemm_taps(Tensor A, Tensor B, Tensor(a!) out, int N, int K, int[] shifts, int padded, int Bn, int H, int W, Tensor? scale_a, Tensor? scale_b) -> ()", &gemm_taps);
   m.def("wgrad_taps(Tensor DY, Tensor X, Tensor(a!) dW, int taps, int Wp) -> ()", &wgrad_taps);
+  m.def("pad_nhwc(Tensor x) -> Tensor", &pad_nhwc);
+  m.def("fp8_scale_update(Tensor(a!) amax, Tensor(b!) scale, Tensor(c!) inv, float target) -> ()", &fp8_scale_update);
+  m.def("conv_weight_prep(Tensor w) -> (Tensor, Tensor)", &conv_weight_prep);
+  m.def("conv_wgrad_unpack(Tensor dw, int Co, int Ci, int k) -> Tensor", &conv_wgrad_unpack);
   m.def("bn_forward(Tensor x, Tensor? res, Tensor gamma, Tensor beta, Tensor(a!)? run_mean, Tensor(b!)? run_var, Tensor(c!) mean, Tensor(d!) invstd, Tensor(e!) sums, Tensor(f!) y, float momentum, float eps, bool relu) -> ()", &bn_forward);
   m.def("bn_backward(Tensor dy, Tensor x, Tensor y, Tensor mean, Tensor invstd, Tensor gamma, Tensor(a!) sums, Tensor(b!) dx, Tensor(c!)? dres, bool relu) -> ()", &bn_backward);
   m.def("avgpool_forward(Tensor x, Tensor(a!) out, int B, int HW, int C) -> ()", &avgpool_forward);

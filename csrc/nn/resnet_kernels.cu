@@ -305,6 +305,23 @@ __global__ void fp8_quantize_kernel(const __nv_bfloat16* __restrict__ x, uint8_t
   if ((threadIdx.x & 31) == 0 && local > 0.f) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(local));   // non-negative floats order as ints
 }
 
+// Delayed scaling bookkeeping of one tensor role in ONE tiny launch (was six ATen element-wise kernels per
+// tensor and step): scale <- (448 / margin) / amax_prev (kept when amax_prev == 0), inv <- 1 / scale, amax <- 0.
+__global__ void fp8_scale_update_kernel(float* __restrict__ amax, float* __restrict__ scale, float* __restrict__ inv,
+                                        float target) {
+  const float a = *amax;
+  float s = *scale;
+  if (a > 0.f) s = target / fmaxf(a, 1e-12f);
+  *scale = s;
+  *inv = 1.0f / s;
+  *amax = 0.f;
+}
+
+void fp8_scale_update(float* amax, float* scale, float* inv, float target, cudaStream_t st) {
+  fp8_scale_update_kernel<<<1, 1, 0, st>>>(amax, scale, inv, target);
+  hefl::cuda::note_launch();
+}
+
 void fp8_quantize(const void* x, uint8_t* q, const float* scale, float* amax, int64_t n, cudaStream_t st) {
   const int64_t n8 = n / 8;
   fp8_quantize_kernel<<<blocks_for(n8, 256 * 4, 148 * 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), q, scale,

@@ -42,10 +42,8 @@ class DelayedScale:
         if not self.ready:                      # first use: take the scale from the data itself
             self.amax.copy_(x.detach().abs().amax().float().reshape(1))
             self.ready = True
-        new = (E4M3_MAX / MARGIN) / self.amax.clamp_min(1e-12)
-        self.scale.copy_(torch.where(self.amax > 0, new, self.scale))
-        torch.reciprocal(self.scale, out=self.inv)
-        self.amax.zero_()
+        # scale <- (448 / margin) / amax (kept if amax == 0), inv <- 1 / scale, amax <- 0: one tiny launch
+        _ext.ops().fp8_scale_update(self.amax, self.scale, self.inv, E4M3_MAX / MARGIN)
 
 
 def _quantize(x2: torch.Tensor, st: DelayedScale) -> torch.Tensor:

@@ -57,29 +57,29 @@ class _Conv1x1TC(torch.autograd.Function):
         B, Cin, H, W = x.shape
         Cout = w.shape[0]
         x2 = _nhwc2d(x)
-        wb = w.reshape(Cout, Cin).to(torch.bfloat16).contiguous()
+        wb, wT = ops.conv_weight_prep(w.detach().contiguous())            # [Cout,Cin] and its transpose, one launch
         y2 = torch.empty(B * H * W, Cout, dtype=torch.bfloat16, device=x.device)
-        if fp8_state is not None:
+        if fp8_state is not None and Cin % 128 == 0:          # an e4m3 k-block is 128 channels (128 bytes)
             sx, sw = fp8_state
             xq = _fp8._quantize(x2, sx).view(torch.uint8)
             wq = _fp8._quantize(wb, sw).view(torch.uint8)
             ops.gemm_taps(xq, wq, y2, Cout, Cin, [], 0, 0, 0, 0, sx.inv, sw.inv)
         else:
             ops.gemm_taps(x2, wb, y2, Cout, Cin, [], 0, 0, 0, 0, None, None)
-        ctx.save_for_backward(x2, wb)
+        ctx.save_for_backward(x2, wT)
         ctx.shape = (B, Cin, H, W, Cout)
         return _as_nchw(y2, B, H, W)
 
     @staticmethod
     def backward(ctx, gy):
         ops = _ext.ops()
-        x2, wb = ctx.saved_tensors
+        x2, wT = ctx.saved_tensors
         B, Cin, H, W, Cout = ctx.shape
         g2 = gy.permute(0, 2, 3, 1).reshape(B * H * W, Cout)
         if g2.dtype != torch.bfloat16 or not g2.is_contiguous():
             g2 = g2.to(torch.bfloat16).contiguous()
         dx2 = torch.empty(B * H * W, Cin, dtype=torch.bfloat16, device=gy.device)
-        ops.gemm_taps(g2, wb.t().contiguous(), dx2, Cin, Cout, [], 0, 0, 0, 0, None, None)     # dX = dY . W
+        ops.gemm_taps(g2, wT, dx2, Cin, Cout, [], 0, 0, 0, 0, None, None)                       # dX = dY . W
         dw = torch.empty(1, Cout, Cin, dtype=torch.float32, device=gy.device)
         ops.wgrad_taps(g2, x2, dw, 1, 0)                                                       # dW = dY^T . X
         return _as_nchw(dx2, B, H, W), dw.view(Cout, Cin, 1, 1), None
@@ -95,27 +95,29 @@ class _Conv3x3TC(torch.autograd.Function):
         ops = _ext.ops()
         B, Cin, H, W = x.shape
         Cout = w.shape[0]
-        xp = F.pad(x.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)).contiguous()                 # [B, H+2, W+2, Cin]
-        wt = w.to(torch.bfloat16).permute(2, 3, 0, 1).reshape(9 * Cout, Cin).contiguous()  # [tap][Cout][Cin]
+        xp = ops.pad_nhwc(x)                                          # [B, H+2, W+2, Cin], zero border, one pass
+        # wt [tap][Cout][Cin] for the forward; wd [tap][Cin][Cout] = filter rotated by 180 degrees, for dgrad
+        wt, wd = ops.conv_weight_prep(w.detach().contiguous())
         y2 = torch.empty(B * H * W, Cout, dtype=torch.bfloat16, device=x.device)
         ops.gemm_taps(xp.view(-1, Cin), wt, y2, Cout, Cin, _shifts(W + 2), 1, B, H, W, None, None)
-        ctx.save_for_backward(xp, w)
+        ctx.save_for_backward(xp, wd)
         ctx.shape = (B, Cin, H, W, Cout)
         return _as_nchw(y2, B, H, W)
 
     @staticmethod
     def backward(ctx, gy):
         ops = _ext.ops()
-        xp, w = ctx.saved_tensors
+        xp, wd = ctx.saved_tensors
         B, Cin, H, W, Cout = ctx.shape
-        gp = F.pad(gy.permute(0, 2, 3, 1).to(torch.bfloat16), (0, 0, 1, 1, 1, 1)).contiguous()   # [B, H+2, W+2, Cout]
+        if gy.dtype != torch.bfloat16 or not gy.is_contiguous(memory_format=torch.channels_last):
+            gy = gy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        gp = ops.pad_nhwc(gy)                                         # [B, H+2, W+2, Cout]
         # dX = conv(dY, W rotated by 180 degrees, channels swapped): tap (r, s) -> W[:, :, 2-r, 2-s]^T
-        wd = w.to(torch.bfloat16).flip(2, 3).permute(2, 3, 1, 0).reshape(9 * Cin, Cout).contiguous()
         dx2 = torch.empty(B * H * W, Cin, dtype=torch.bfloat16, device=gy.device)
         ops.gemm_taps(gp.view(-1, Cout), wd, dx2, Cin, Cout, _shifts(W + 2), 1, B, H, W, None, None)
         dw = torch.empty(9, Cout, Cin, dtype=torch.float32, device=gy.device)
         ops.wgrad_taps(gp.view(-1, Cout), xp.view(-1, Cin), dw, 9, W + 2)
-        return _as_nchw(dx2, B, H, W), dw.view(3, 3, Cout, Cin).permute(2, 3, 0, 1).contiguous()
+        return _as_nchw(dx2, B, H, W), ops.conv_wgrad_unpack(dw, Cout, Cin, 3)
 
 
 def conv1x1(x: torch.Tensor, w: torch.Tensor, stride: int = 1, fp8_state=None) -> torch.Tensor:

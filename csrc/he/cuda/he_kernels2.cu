@@ -242,6 +242,7 @@ struct EncArgs {
   uint32_t ct_offset;
   int L;
   int64_t C;
+  uint64_t* scratch;        // N = 16384 only: [grid][N] words for u_hat
 };
 
 __device__ __forceinline__ uint32_t pack_e(int e0, int e1) { return ((uint32_t)e0 & 0xFFu) | (((uint32_t)e1 & 0xFFu) << 8); }
@@ -251,9 +252,12 @@ __device__ __forceinline__ int unpack_e1(uint32_t p) { return (int)(int8_t)((p >
 // last forward pass of NTT(e + ...) fused with  c = reduce(u_hat * pk + a_hat)  and the store.
 // The thread owns E = 8 or 16 contiguous coefficients; the epilogue walks them four at a time so
 // that only 4 (pk, pk') pairs and 4 words of u_hat are live next to the E accumulators.
-template <int LOGN>
-__device__ __forceinline__ void enc_epilogue(uint32_t bufA, uint32_t bufU, const Limb& T, const uint64_t* pkx_limb,
-                                             uint64_t* ct, int64_t c_first, int64_t C, int which, int L, int limb) {
+// USCR: u_hat does not fit in shared memory next to the working buffer (N = 16384): it lives in a per-CTA
+// global scratch row that the same thread wrote with the same geometry (L2 resident, coherent loads).
+template <int LOGN, bool USCR>
+__device__ __forceinline__ void enc_epilogue(uint32_t bufA, uint32_t bufU, const uint64_t* uscr, const Limb& T,
+                                             const uint64_t* pkx_limb, uint64_t* ct, int64_t c_first, int64_t C,
+                                             int which, int L, int limb) {
   constexpr int NP = num_passes(LOGN);
   constexpr int N = 1 << LOGN;
   using GG = Geo<LOGN, NP - 1>;
@@ -275,8 +279,15 @@ __device__ __forceinline__ void enc_epilogue(uint32_t bufA, uint32_t bufU, const
       uint64_t pk[2][4], uh[4], r[4];
       ldg256(pp + 8 * v, pk[0]);
       ldg256(pp + 8 * v + 4, pk[1]);
-      lds128(bufU + row + (((ch0 + 2 * v) ^ rs) << 4), uh[0], uh[1]);
-      lds128(bufU + row + (((ch0 + 2 * v + 1) ^ rs) << 4), uh[2], uh[3]);
+      if constexpr (USCR) {
+        asm volatile("ld.global.v4.u64 {%0, %1, %2, %3}, [%4];"
+                     : "=l"(uh[0]), "=l"(uh[1]), "=l"(uh[2]), "=l"(uh[3])
+                     : "l"(uscr + G.base + 4 * v)
+                     : "memory");
+      } else {
+        lds128(bufU + row + (((ch0 + 2 * v) ^ rs) << 4), uh[0], uh[1]);
+        lds128(bufU + row + (((ch0 + 2 * v + 1) ^ rs) << 4), uh[2], uh[3]);
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint64_t t = mul_shoup_lazy(uh[k], pk[k >> 1][(k & 1) * 2], pk[k >> 1][(k & 1) * 2 + 1], T.q);
@@ -296,9 +307,10 @@ encrypt2_kernel(const __grid_constant__ CUtensorMap tmap, EncArgs a) {
   constexpr int NP = num_passes(LOGN);
   constexpr int POLYS = (1 << unit_log(LOGN)) >> LOGN;
   constexpr int N = 1 << LOGN;
-  using S = Smem<LOGN, 2>;
+  constexpr bool USCR = LOGN >= 14;                 // one working buffer in shared memory, u_hat in global scratch
+  using S = Smem<LOGN, USCR ? 1 : 2>;
   using G0 = Geo<LOGN, 0>;
-  static_assert(G0::PER_THREAD == 1, "the first pass must be one radix-16 group per thread");
+  constexpr int PT = G0::PER_THREAD;                // radix-16 groups per thread in the first pass (1, or 2 at N = 16384)
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
@@ -313,7 +325,9 @@ encrypt2_kernel(const __grid_constant__ CUtensorMap tmap, EncArgs a) {
   const Limb T = make_limb(sbase + S::kTw, a.tw2 + (size_t)(W.limb * 2) * N * 2, a.consts, W.limb);
   const Modulus m{T.q, a.consts[W.limb * 8 + 1], a.consts[W.limb * 8 + 2]};
   const uint64_t sc = a.msg_scale ? a.msg_scale[W.limb] : 1;
-  const uint32_t bufU = sbase + S::kBuf, bufA = bufU + unit_bytes(LOGN);
+  const uint32_t bufU = sbase + S::kBuf;
+  const uint32_t bufA = USCR ? bufU : bufU + unit_bytes(LOGN);
+  uint64_t* uscr = USCR ? a.scratch + (size_t)blockIdx.x * (1u << unit_log(LOGN)) : nullptr;
   const uint64_t* pk0 = a.pkx + ((size_t)(0 * a.L + W.limb) * N) * 2;
   const uint64_t* pk1 = a.pkx + ((size_t)(1 * a.L + W.limb) * N) * 2;
   mbar_wait(&bars[0], 0);
@@ -321,35 +335,53 @@ encrypt2_kernel(const __grid_constant__ CUtensorMap tmap, EncArgs a) {
   const int64_t units = (a.C + POLYS - 1) / POLYS;
   for (int64_t u = W.worker; u < units; u += W.nworkers) {
     const int64_t c_first = u * POLYS;
-    const G0 G(tid);
-    const uint32_t ctid = a.ct_offset + (uint32_t)(c_first + G.poly);
-    uint32_t epack[8];
+    uint32_t epack[PT][8];
     // ---- phase 1: u_hat = NTT(u), sampled straight into the registers of the first pass ----
-    {
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      const G0 G(tid + j * kThreads);
+      const uint32_t ctid = a.ct_offset + (uint32_t)(c_first + G.poly);
       uint64_t x[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const EncNoise z = sample_enc_noise(a.seed, ctid, G.coef + ((uint32_t)k << G0::TL));
         x[k] = lift_signed(z.u, T.q);
         const uint32_t pe = pack_e(z.e0, z.e1);
-        if (k & 1) epack[k >> 1] |= pe << 16; else epack[k >> 1] = pe;
+        if (k & 1) epack[j][k >> 1] |= pe << 16; else epack[j][k >> 1] = pe;
       }
       fwd_butterflies<G0::ST, G0::R>(x, G.high, T);
       group_store<LOGN, 0>(bufU, G, x);
+    }
+    compute_sync();
+    fwd_pass_smem<LOGN, 1>(bufU, T);
+    if constexpr (NP >= 4) fwd_pass_smem<LOGN, 2>(bufU, T);
+    if constexpr (!USCR) {
+      fwd_pass_smem<LOGN, NP - 1>(bufU, T);
+    } else {
+      // last pass straight to the global scratch row (same geometry as the epilogues that read it back)
+      using GL = Geo<LOGN, NP - 1>;
+#pragma unroll 1
+      for (int j = 0; j < GL::PER_THREAD; ++j) {
+        const GL G(tid + j * kThreads);
+        uint64_t x[GL::E];
+        group_load<LOGN, NP - 1>(bufU, G, x);
+        fwd_butterflies<GL::ST, GL::R>(x, G.high, T);
+#pragma unroll
+        for (int v = 0; v < GL::E / 4; ++v) stg256(uscr + G.base + 4 * v, x[4 * v], x[4 * v + 1], x[4 * v + 2], x[4 * v + 3]);
+      }
       compute_sync();
-      fwd_pass_smem<LOGN, 1>(bufU, T);
-      if constexpr (NP >= 3) fwd_pass_smem<LOGN, 2>(bufU, T);
-      if constexpr (NP >= 4) fwd_pass_smem<LOGN, 3>(bufU, T);
     }
     // ---- phase 2: c0 = u_hat * pk0 + NTT(e0 + m) ----
-    {
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      const G0 G(tid + j * kThreads);
       uint64_t x[16];
       const int64_t c = c_first + G.poly;
       const bool have_msg = a.msg != nullptr && c < a.C;
       const int64_t* mrow = a.msg + (have_msg ? c * N : 0);
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
-        const uint32_t pe = (k & 1) ? (epack[k >> 1] >> 16) : epack[k >> 1];
+        const uint32_t pe = (k & 1) ? (epack[j][k >> 1] >> 16) : epack[j][k >> 1];
         uint64_t v = lift_signed(unpack_e0(pe), T.q);
         if (have_msg) {
           uint64_t mm = reduce_signed(mrow[G.coef + ((uint32_t)k << G0::TL)], m);
@@ -360,26 +392,28 @@ encrypt2_kernel(const __grid_constant__ CUtensorMap tmap, EncArgs a) {
       }
       fwd_butterflies<G0::ST, G0::R>(x, G.high, T);
       group_store<LOGN, 0>(bufA, G, x);
-      compute_sync();
-      if constexpr (NP >= 3) fwd_pass_smem<LOGN, 1>(bufA, T);
-      if constexpr (NP >= 4) fwd_pass_smem<LOGN, 2>(bufA, T);
-      enc_epilogue<LOGN>(bufA, bufU, T, pk0, a.ct, c_first, a.C, 0, a.L, W.limb);
     }
+    compute_sync();
+    if constexpr (NP >= 3) fwd_pass_smem<LOGN, 1>(bufA, T);
+    if constexpr (NP >= 4) fwd_pass_smem<LOGN, 2>(bufA, T);
+    enc_epilogue<LOGN, USCR>(bufA, bufU, uscr, T, pk0, a.ct, c_first, a.C, 0, a.L, W.limb);
     // ---- phase 3: c1 = u_hat * pk1 + NTT(e1) ----
-    {
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      const G0 G(tid + j * kThreads);
       uint64_t x[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
-        const uint32_t pe = (k & 1) ? (epack[k >> 1] >> 16) : epack[k >> 1];
+        const uint32_t pe = (k & 1) ? (epack[j][k >> 1] >> 16) : epack[j][k >> 1];
         x[k] = lift_signed(unpack_e1(pe), T.q);
       }
       fwd_butterflies<G0::ST, G0::R>(x, G.high, T);
       group_store<LOGN, 0>(bufA, G, x);
-      compute_sync();
-      if constexpr (NP >= 3) fwd_pass_smem<LOGN, 1>(bufA, T);
-      if constexpr (NP >= 4) fwd_pass_smem<LOGN, 2>(bufA, T);
-      enc_epilogue<LOGN>(bufA, bufU, T, pk1, a.ct, c_first, a.C, 1, a.L, W.limb);
     }
+    compute_sync();
+    if constexpr (NP >= 3) fwd_pass_smem<LOGN, 1>(bufA, T);
+    if constexpr (NP >= 4) fwd_pass_smem<LOGN, 2>(bufA, T);
+    enc_epilogue<LOGN, USCR>(bufA, bufU, uscr, T, pk1, a.ct, c_first, a.C, 1, a.L, W.limb);
   }
   cluster_sync_all();
 }
@@ -614,12 +648,22 @@ bool dispatch_ntt2(uint64_t* data, int64_t rows, int L, const uint64_t* tw2, con
 }
 
 template <int LOGN>
-void launch_encrypt2(const EncArgs& a, cudaStream_t st) {
+void launch_encrypt2(EncArgs a, cudaStream_t st) {
   constexpr int N = 1 << LOGN;
+  constexpr int NBUF = LOGN >= 14 ? 1 : 2;
   const CUtensorMap tmap = rows128_map(a.tw2, (uint64_t)a.L * 2 * N * 16, tw_rows(LOGN) / 2);
   auto k = encrypt2_kernel<LOGN>;
-  set_smem(k, Smem<LOGN, 2>::kTotal);
-  k<<<grid_ctas(1), kThreads, Smem<LOGN, 2>::kTotal, st>>>(tmap, a);
+  set_smem(k, Smem<LOGN, NBUF>::kTotal);
+  const int grid = grid_ctas(1);
+  if (LOGN >= 14) {
+    // u_hat of the ciphertext in flight: one row per CTA, allocated once per device (19 MB for 148 CTAs), L2 resident
+    static uint64_t* scratch[16] = {nullptr};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!scratch[dev & 15]) cudaMalloc(&scratch[dev & 15], (size_t)sm_count() * N * 8);
+    a.scratch = scratch[dev & 15];
+  }
+  k<<<grid, kThreads, Smem<LOGN, NBUF>::kTotal, st>>>(tmap, a);
 }
 
 template <int LOGN, unsigned CORR>
@@ -685,21 +729,22 @@ bool encrypt2(const int64_t* msg, const uint64_t* pkx, uint64_t* ct, int64_t C, 
               const uint64_t* consts, const uint64_t* msg_scale, uint64_t seed, uint32_t ct_offset, int qbits,
               cudaStream_t st) {
   if (C == 0) return true;
-  if (!ntt2_supported(logn, L, qbits) || logn > 13) return false;
+  if (!ntt2_supported(logn, L, qbits)) return false;
   {
     // A persistent CTA wants at least two units of 8192 coefficients: below that (the 109
     // ciphertexts of the medical CNN) the one-CTA-per-(ciphertext, limb) kernel fills the GPU
     // better (measured 0.107 vs 0.131 ms at n = 4096, L = 3, C = 109).
-    const int64_t units = (C * (1ll << logn) + 8191) / 8192;
+    const int64_t units = logn >= 13 ? C : (C * (1ll << logn) + 8191) / 8192;
     const int64_t workers = (grid_ctas(1) / 2 / L) * 2;
     if (units < 2 * workers) return false;
   }
-  const EncArgs a{msg, pkx, ct, tw2, consts, msg_scale, seed, ct_offset, L, C};
+  const EncArgs a{msg, pkx, ct, tw2, consts, msg_scale, seed, ct_offset, L, C, nullptr};
   switch (logn) {
     case 10: launch_encrypt2<10>(a, st); break;
     case 11: launch_encrypt2<11>(a, st); break;
     case 12: launch_encrypt2<12>(a, st); break;
     case 13: launch_encrypt2<13>(a, st); break;
+    case 14: launch_encrypt2<14>(a, st); break;
   }
   note_launch();
   return true;

@@ -310,7 +310,7 @@ void encrypt_out(const c10::optional<Tensor>& msg, const Tensor& pk, int64_t C, 
   if (pk.is_cuda()) {
     if (fast_path_enabled() && tables.size(0) == L) {
       const TableExt& te = table_ext(tables, consts);
-      if (hefl::cuda::ntt2_supported((int)logn, (int)L, te.qbits) && logn <= 13) {
+      if (hefl::cuda::ntt2_supported((int)logn, (int)L, te.qbits) && logn <= 14) {
         const Tensor& pkx = key_ext(pk, consts, L);
         if (hefl::cuda::encrypt2(mp, u64(pkx), u64(ct), C, (int)L, (int)logn, u64(te.tw2), u64(consts),
                                  u64o(msg_scale), (uint64_t)seed, (uint32_t)ct_offset, te.qbits, cur_stream()))

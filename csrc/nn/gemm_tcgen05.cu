@@ -472,17 +472,29 @@ __global__ void pad_nhwc_kernel(const uint4* __restrict__ x, uint4* __restrict__
 }
 
 // w fp32 [Co][Ci][3][3] -> wt bf16 [tap][Co][Ci] (forward) and wd bf16 [tap][Ci][Co] with the filter rotated by 180
-// degrees (dgrad); for k = 1: wt [Co][Ci] and wd = its transpose [Ci][Co]
-__global__ void conv_weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wt,
-                                        __nv_bfloat16* __restrict__ wd, int Co, int Ci, int kk) {
-  const int64_t total = (int64_t)kk * Co * Ci;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ci = (int)(i % Ci);
-    const int co = (int)((i / Ci) % Co);
-    const int tap = (int)(i / ((int64_t)Ci * Co));
-    const __nv_bfloat16 v = __float2bfloat16(w[((int64_t)co * Ci + ci) * kk + tap]);
-    wt[i] = v;
-    if (wd) wd[((int64_t)(kk - 1 - tap) * Ci + ci) * Co + co] = v;
+// degrees (dgrad); for k = 1: wt [Co][Ci] and wd = its transpose [Ci][Co]. One 32 x 32 (co, ci) tile per block and
+// tap, transposed through shared memory so that both outputs are written with unit stride.
+__global__ void __launch_bounds__(256)
+conv_weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wt, __nv_bfloat16* __restrict__ wd,
+                        int Co, int Ci, int kk) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int tap = blockIdx.z;
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // 32 x 8
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int co = co0 + ty + 8 * r, ci = ci0 + tx;
+    if (co < Co && ci < Ci) {
+      const __nv_bfloat16 v = __float2bfloat16(w[((int64_t)co * Ci + ci) * kk + tap]);
+      tile[ty + 8 * r][tx] = v;
+      wt[((int64_t)tap * Co + co) * Ci + ci] = v;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int ci = ci0 + ty + 8 * r, co = co0 + tx;
+    if (co < Co && ci < Ci) wd[((int64_t)(kk - 1 - tap) * Ci + ci) * Co + co] = tile[tx][ty + 8 * r];
   }
 }
 
@@ -508,10 +520,8 @@ void pad_nhwc(const void* x, void* xp, int B, int H, int W, int C, cudaStream_t 
 }
 
 void conv_weight_prep(const float* w, void* wt, void* wd, int Co, int Ci, int kk, cudaStream_t st) {
-  const int64_t total = (int64_t)kk * Co * Ci;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  conv_weight_prep_kernel<<<blocks, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(wt), reinterpret_cast<__nv_bfloat16*>(wd), Co, Ci, kk);
+  dim3 grid((Ci + 31) / 32, (Co + 31) / 32, kk);
+  conv_weight_prep_kernel<<<grid, 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16*>(wt), reinterpret_cast<__nv_bfloat16*>(wd), Co, Ci, kk);
   hefl::cuda::note_launch();
 }
 

@@ -275,6 +275,171 @@ void launch_kmajor(const void* A, const void* Bm, const GemmArgs& a, int64_t a_r
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Block-scaled e4m3 GEMM (kind::mxf8f6f4.block_scale): one UE8M0 scale per row and per 32 elements of K
+// ------------------------------------------------------------------------------------------------------------
+// C[M, N] = sum_k (A[m, k] 2^(sa[m, k/32] - 127)) (B[n, k] 2^(sb[n, k/32] - 127)). A, B: e4m3 bytes, K-major.
+// Scale factors travel in the layout the tensor core wants: for every (128-row block, group of four 32-element
+// k-blocks) one 512-byte tile [lane l = 0..31][row quarter i = 0..3][k-block kb = 0..3] holding the scale of row
+// 32*i + l -- a stage brings its two tiles in with a bulk copy, `tcgen05.cp.32x128b.warpx4` replicates each into
+// four TMEM columns, and the instruction descriptor of MMA kb selects byte kb of those columns (a_sf_id / b_sf_id).
+struct MxArgs {
+  int m_tiles, n_tiles, kgroups;   // 128-row tiles, BN-column tiles, K / 128
+  int n_total;
+  int64_t m_rows;
+  __nv_bfloat16* C;
+  const uint8_t* sfa;              // [m_tiles][kgroups][512]
+  const uint8_t* sfb;              // [N / 128][kgroups][512]
+  uint32_t idesc;                  // instruction descriptor without the scale-factor ids
+};
+
+constexpr int kMxStage = 128 * 128 + 128 * 128 + 1024;    // A tile, B tile, two scale tiles
+constexpr int kMxStages = 5;
+constexpr int kMxSmem = kMxStages * kMxStage + 256 + 1024;
+
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// 32 rows x 16 bytes, no swizzle: four 8-row core matrices 128 bytes apart
+__device__ __forceinline__ uint64_t sf_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((128u >> 4) & 0x3FFF) << 32;     // SBO
+  d |= 1ull << 46;
+  return d;
+}
+__device__ __forceinline__ void utccp_32x128b_warpx4(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+__device__ __forceinline__ void umma_mxf8(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                          uint32_t idesc, uint32_t tsfa, uint32_t tsfb, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %8, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], da, db, %5, [%6], [%7], p;\n\t}"
+      ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(tsfa), "r"(tsfb), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1)
+mx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const MxArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kMxStages * kMxStage);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMxStages;
+  uint64_t* tfull = empty + kMxStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int BN = 128;
+  constexpr uint32_t SFA_COL = 2 * BN, SFB_COL = 2 * BN + 4;
+  if (warp == 4 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < kMxStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_tiles = a.m_tiles * a.n_tiles;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      int st = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int mb = t / a.n_tiles, nb = t - mb * a.n_tiles;
+        for (int kg = 0; kg < a.kgroups; ++kg) {
+          mbar_wait(&empty[st], phase ^ 1u);
+          uint8_t* s = smem + st * kMxStage;
+          mbar_expect_tx(&full[st], kMxStage);
+          tma_load_2d(s, &tmA, kg * 128, mb * 128, &full[st]);
+          tma_load_2d(s + 16384, &tmB, kg * 128, nb * BN, &full[st]);
+          bulk_load_1d(s + 32768, a.sfa + ((size_t)mb * a.kgroups + kg) * 512, 512, &full[st]);
+          bulk_load_1d(s + 32768 + 512, a.sfb + ((size_t)nb * a.kgroups + kg) * 512, 512, &full[st]);
+          if (++st == kMxStages) { st = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    constexpr uint32_t hi = desc_hi(8 * 128, 128);
+    int st = 0;
+    uint32_t phase = 0;
+    int tb = 0;
+    uint32_t tb_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(&tempty[tb], tb_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + tb * BN;
+      for (int kg = 0; kg < a.kgroups; ++kg) {
+        mbar_wait(&full[st], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          uint8_t* s = smem + st * kMxStage;
+          const uint32_t a_lo = desc_lo(smem_u32(s));
+          const uint32_t b_lo = desc_lo(smem_u32(s + 16384));
+          utccp_32x128b_warpx4(tmem_base + SFA_COL, sf_desc(smem_u32(s + 32768)));
+          utccp_32x128b_warpx4(tmem_base + SFB_COL, sf_desc(smem_u32(s + 32768 + 512)));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t idesc = a.idesc | ((uint32_t)k << 4) | ((uint32_t)k << 29);      // b_sf_id, a_sf_id
+            umma_mxf8(d_tmem, a_lo + k * 2, hi, b_lo + k * 2, hi, idesc, tmem_base + SFA_COL, tmem_base + SFB_COL,
+                      (kg | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[st]);
+          if (kg == a.kgroups - 1) umma_commit(&tfull[tb]);
+        }
+        __syncwarp();
+        if (++st == kMxStages) { st = 0; phase ^= 1u; }
+      }
+      if (++tb == 2) { tb = 0; tb_phase ^= 1u; }
+    }
+  } else {
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    int tb = 0;
+    uint32_t tb_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int mb = t / a.n_tiles, nb = t - mb * a.n_tiles;
+      const int64_t m = (int64_t)mb * 128 + warp * 32 + lane;
+      const bool valid = m < a.m_rows;
+      mbar_wait(&tfull[tb], tb_phase);
+      tc_fence_after();
+      __nv_bfloat16* dst = a.C + m * a.n_total + nb * BN;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        float v[32];
+        tmem_ld32(tmem_base + lane_base + tb * BN + ch * 32, v);
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 8)
+            *reinterpret_cast<uint4*>(dst + ch * 32 + c) = make_uint4(pack_bf16x2(v[c], v[c + 1]), pack_bf16x2(v[c + 2], v[c + 3]),
+                                                                       pack_bf16x2(v[c + 4], v[c + 5]), pack_bf16x2(v[c + 6], v[c + 7]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[tb]);
+      if (++tb == 2) { tb = 0; tb_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // wgrad: MN-major operands (pixel axis = K), up to 3 taps per CTA, split over pixel ranges
 // ------------------------------------------------------------------------------------------------------------
 struct WgArgs {
@@ -530,6 +695,33 @@ void conv_wgrad_unpack(const float* dw, float* g, int Co, int Ci, int kk, cudaSt
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   conv_wgrad_unpack_kernel<<<blocks, 256, 0, st>>>(dw, g, Co, Ci, kk);
+  hefl::cuda::note_launch();
+}
+
+// Block-scaled e4m3 GEMM; sfa / sfb in the tiled layout described at MxArgs. idesc_variant selects the encoding of
+// the M field of the block-scaled instruction descriptor (0: M >> 7 at bit 27, the documented layout; 1: M >> 4 at bit 24).
+void gemm_mxfp8(const void* A, const void* Bm, const void* sfa, const void* sfb, void* C, int64_t M, int N, int K,
+                int idesc_variant, cudaStream_t st) {
+  if (K % 128 != 0 || N % 128 != 0) throw std::runtime_error("gemm_mxfp8: K and N must be multiples of 128");
+  MxArgs a{};
+  a.m_tiles = (int)((M + 127) / 128);
+  a.n_tiles = N / 128;
+  a.kgroups = K / 128;
+  a.n_total = N;
+  a.m_rows = M;
+  a.C = reinterpret_cast<__nv_bfloat16*>(C);
+  a.sfa = reinterpret_cast<const uint8_t*>(sfa);
+  a.sfb = reinterpret_cast<const uint8_t*>(sfb);
+  // e4m3 x e4m3 (formats 0), K-major both, N >> 3 at bit 17, UE8M0 scales (bit 23)
+  uint32_t idesc = ((uint32_t)(128 >> 3) << 17) | (1u << 23);
+  idesc |= idesc_variant == 0 ? ((uint32_t)(128 >> 7) << 27) : ((uint32_t)(128 >> 4) << 24);
+  a.idesc = idesc;
+  const CUtensorMap tmA = map2d(A, 1, (uint64_t)K, (uint64_t)M, (uint64_t)K, 128, 128);
+  const CUtensorMap tmB = map2d(Bm, 1, (uint64_t)K, (uint64_t)N, (uint64_t)K, 128, 128);
+  cudaFuncSetAttribute(mx_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMxSmem);
+  const int tiles = a.m_tiles * a.n_tiles;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  mx_gemm_kernel<<<grid, 192, kMxSmem, st>>>(tmA, tmB, a);
   hefl::cuda::note_launch();
 }
 

@@ -47,6 +47,8 @@ void gemm_taps(const void* A, const void* Bm, void* C, int64_t a_rows, int N, in
 // dW[taps][Co][Ci] (fp32, zeroed by the caller) += dY[rows, Co]^T . X[rows + shift(tap), Ci]; taps = 1, or 9 on a padded
 // grid whose rows are Wp pixels long.
 void wgrad_taps(const void* DY, const void* X, float* dW, int64_t rows, int Co, int Ci, int taps, int Wp, cudaStream_t st);
+void gemm_mxfp8(const void* A, const void* Bm, const void* sfa, const void* sfb, void* C, int64_t M, int N, int K,
+                int idesc_variant, cudaStream_t st);
 void pad_nhwc(const void* x, void* xp, int B, int H, int W, int C, cudaStream_t st);          // bf16, zero border of 1
 void conv_weight_prep(const float* w, void* wt, void* wd, int Co, int Ci, int kk, cudaStream_t st);
 void conv_wgrad_unpack(const float* dw, float* g, int Co, int Ci, int kk, cudaStream_t st);
@@ -59,6 +61,8 @@ void bn_backward(const void* dy, const void* x, const void* y, const float* mean
 void avgpool_forward(const void* x, float* out, int B, int HW, int C, cudaStream_t st);
 void avgpool_backward(const float* dout, void* dx, int B, int HW, int C, cudaStream_t st);
 void fp8_quantize(const void* x, uint8_t* q, const float* scale, float* amax, int64_t n, cudaStream_t st);
+// bf16 [R,K] -> e4m3 [R,K] + UE8M0 scale tiles [ceil(R/128)][K/128][512] (rows beyond R must be pre-set by the caller)
+void mxfp8_quantize(const void* x, uint8_t* q, uint8_t* sf, int64_t R, int K, cudaStream_t st);
 void fp8_scale_update(float* amax, float* scale, float* inv, float target, cudaStream_t st);
 void umma_shift_probe(const void* A, const void* Bm, float* out, int CK, int shift_rows, int mode, cudaStream_t st);
 

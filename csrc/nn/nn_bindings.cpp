@@ -291,6 +291,28 @@ void wgrad_taps(const Tensor& DY, const Tensor& X, Tensor dW, int64_t taps, int6
   hefl::nn::wgrad_taps(DY.data_ptr(), X.data_ptr(), dW.data_ptr<float>(), DY.size(0), (int)Co, (int)Ci, (int)taps, (int)Wp, cur());
 }
 
+// out [M,N] bf16 = block-scaled e4m3 GEMM (kind::mxf8f6f4.block_scale); sfa / sfb: uint8 tiles [rows/128][K/128][512]
+void gemm_mxfp8(const Tensor& A, const Tensor& Bm, const Tensor& sfa, const Tensor& sfb, Tensor out, int64_t variant) {
+  TORCH_CHECK(A.is_cuda() && A.element_size() == 1 && Bm.element_size() == 1 && A.dim() == 2 && Bm.dim() == 2 &&
+              A.is_contiguous() && Bm.is_contiguous() && A.size(1) == Bm.size(1), "A [M,K], B [N,K] e4m3 bytes");
+  const int64_t M = A.size(0), K = A.size(1), N = Bm.size(0);
+  TORCH_CHECK(out.scalar_type() == at::kBFloat16 && out.numel() == M * N && out.is_contiguous(), "out [M,N] bf16");
+  TORCH_CHECK(sfa.numel() == ((M + 127) / 128) * (K / 128) * 512 && sfb.numel() == (N / 128) * (K / 128) * 512 &&
+              sfa.is_contiguous() && sfb.is_contiguous(), "scale-factor tiles have the wrong size");
+  hefl::nn::gemm_mxfp8(A.data_ptr(), Bm.data_ptr(), sfa.data_ptr(), sfb.data_ptr(), out.data_ptr(), M, (int)N, (int)K, (int)variant, cur());
+}
+
+// x bf16 [R,K] (K % 128 == 0) -> (e4m3 bytes [R,K], UE8M0 scale tiles uint8 [ceil(R/128) * K/128 * 512])
+std::tuple<Tensor, Tensor> mxfp8_quantize(const Tensor& x) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.dim() == 2 && x.is_contiguous() && x.size(1) % 128 == 0,
+              "bf16 [R,K] with K a multiple of 128");
+  const int64_t R = x.size(0), K = x.size(1);
+  Tensor q = at::empty({R, K}, x.options().dtype(at::kByte));
+  Tensor sf = at::full({((R + 127) / 128) * (K / 128) * 512}, 127, x.options().dtype(at::kByte));
+  hefl::nn::mxfp8_quantize(x.data_ptr(), q.data_ptr<uint8_t>(), sf.data_ptr<uint8_t>(), R, (int)K, cur());
+  return {q, sf};
+}
+
 void fp8_scale_update(Tensor amax, Tensor scale, Tensor inv, double target) {
   TORCH_CHECK(amax.is_cuda() && amax.scalar_type() == at::kFloat && scale.scalar_type() == at::kFloat && inv.scalar_type() == at::kFloat,
               "fp32 CUDA scalars expected");
@@ -408,6 +430,8 @@ TORCH_LIBRARY_FRAGMENT(hefl, m) {
   m.def("gemm_taps(Tensor A, Tensor B, Tensor(a!) out, int N, int K, int[] shifts, int padded, int Bn, int H, int W, Tensor? scale_a, Tensor? scale_b) -> ()", &gemm_taps);
   m.def("wgrad_taps(Tensor DY, Tensor X, Tensor(a!) dW, int taps, int Wp) -> ()", &wgrad_taps);
   m.def("pad_nhwc(Tensor x) -> Tensor", &pad_nhwc);
+  m.def("mxfp8_quantize(Tensor x) -> (Tensor, Tensor)", &mxfp8_quantize);
+  m.def("gemm_mxfp8(Tensor A, Tensor B, Tensor sfa, Tensor sfb, Tensor(a!) out, int variant) -> ()", &gemm_mxfp8);
   m.def("fp8_scale_update(Tensor(a!) amax, Tensor(b!) scale, Tensor(c!) inv, float target) -> ()", &fp8_scale_update);
   m.def("conv_weight_prep(Tensor w) -> (Tensor, Tensor)", &conv_weight_prep);
   m.def("conv_wgrad_unpack(Tensor dw, int Co, int Ci, int k) -> Tensor", &conv_wgrad_unpack);

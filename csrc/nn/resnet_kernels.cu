@@ -305,6 +305,65 @@ __global__ void fp8_quantize_kernel(const __nv_bfloat16* __restrict__ x, uint8_t
   if ((threadIdx.x & 31) == 0 && local > 0.f) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(local));   // non-negative floats order as ints
 }
 
+// MX (block-scaled) e4m3 quantiser: one UE8M0 scale per row and per 32 consecutive elements of K. One thread per
+// block of 32 (64 bytes in, 32 bytes out); consecutive lanes take consecutive blocks of a row. The scale bytes are
+// written straight in the tile order the tensor core consumes (gemm_tcgen05.cu, MxArgs): per (128-row block,
+// 128-element k-group) 512 bytes [lane l][row quarter i][k-block kb] for row 32*i + l.
+__global__ void mxfp8_quantize_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ q, uint8_t* __restrict__ sf,
+                                      int64_t R, int K) {
+  const int kblocks = K >> 5, kgroups = K >> 7;
+  const int64_t total = R * kblocks;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / kblocks;
+    const int kbk = (int)(t - r * kblocks);
+    const uint4* src = reinterpret_cast<const uint4*>(x + r * K + kbk * 32);
+    uint4 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = src[i];
+    float f[32];
+    float amax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f[8 * i + 2 * j] = __uint_as_float(w[j] << 16);
+        f[8 * i + 2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+        amax = fmaxf(amax, fmaxf(fabsf(f[8 * i + 2 * j]), fabsf(f[8 * i + 2 * j + 1])));
+      }
+    }
+    // smallest e with amax * 2^-e <= 448 (the largest e4m3 magnitude)
+    int e = -127;
+    if (amax > 0.f) {
+      e = (int)((__float_as_uint(amax) >> 23) & 0xFFu) - 127 - 8;
+      if (e < -127) e = -127;
+      const float probe = amax * __uint_as_float((uint32_t)(127 - e) << 23);
+      if (probe > 448.f) ++e;
+      if (e > 127) e = 127;
+    }
+    const float inv = __uint_as_float((uint32_t)(127 - e) << 23);        // 2^-e
+    uint32_t out[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const __nv_fp8x2_storage_t lo = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * i] * inv, f[4 * i + 1] * inv), __NV_SATFINITE, __NV_E4M3);
+      const __nv_fp8x2_storage_t hi = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * i + 2] * inv, f[4 * i + 3] * inv), __NV_SATFINITE, __NV_E4M3);
+      out[i] = (uint32_t)lo | ((uint32_t)hi << 16);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(q + r * K + kbk * 32);
+    dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+    dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+    const int64_t mb = r >> 7;
+    const int rr = (int)(r & 127), l = rr & 31, qi = rr >> 5;
+    sf[((mb * kgroups + (kbk >> 2)) * 32 + l) * 16 + qi * 4 + (kbk & 3)] = (uint8_t)(e + 127);
+  }
+}
+
+void mxfp8_quantize(const void* x, uint8_t* q, uint8_t* sf, int64_t R, int K, cudaStream_t st) {
+  const int64_t total = R * (K >> 5);
+  mxfp8_quantize_kernel<<<blocks_for(total, 256, 148 * 16), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), q, sf, R, K);
+  hefl::cuda::note_launch();
+}
+
 // Delayed scaling bookkeeping of one tensor role in ONE tiny launch (was six ATen element-wise kernels per
 // tensor and step): scale <- (448 / margin) / amax_prev (kept when amax_prev == 0), inv <- 1 / scale, amax <- 0.
 __global__ void fp8_scale_update_kernel(float* __restrict__ amax, float* __restrict__ scale, float* __restrict__ inv,

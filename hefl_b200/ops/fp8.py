@@ -92,12 +92,8 @@ class Conv1x1(nn.Conv2d):
         from . import tc_conv
 
         if (tc_conv.ENABLE if self.use_tc is None else self.use_tc) and tc_conv.eligible(x, self.in_channels, self.out_channels):
-            st = None
-            if on:
-                if self._fp8_state is None:
-                    self._fp8_state = (DelayedScale(x.device), DelayedScale(x.device))
-                st = self._fp8_state
-            return tc_conv.conv1x1(x, self.weight, self.stride[0], st)
+            # fp8 on the hand-written path = block-scaled e4m3 (MX): scales come from the data of this very call
+            return tc_conv.conv1x1(x, self.weight, self.stride[0], "mx" if on else None)
         ok = (on and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4
               and self.in_channels % 16 == 0 and self.out_channels % 16 == 0)
         if not ok:

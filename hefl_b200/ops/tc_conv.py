@@ -59,7 +59,13 @@ class _Conv1x1TC(torch.autograd.Function):
         x2 = _nhwc2d(x)
         wb, wT = ops.conv_weight_prep(w.detach().contiguous())            # [Cout,Cin] and its transpose, one launch
         y2 = torch.empty(B * H * W, Cout, dtype=torch.bfloat16, device=x.device)
-        if fp8_state is not None and Cin % 128 == 0:          # an e4m3 k-block is 128 channels (128 bytes)
+        mx = fp8_state == "mx" and Cin % 128 == 0 and Cout % 128 == 0
+        if mx:
+            # block-scaled e4m3 (kind::mxf8f6f4.block_scale): one UE8M0 scale per row and 32 channels, no amax history
+            xq, xs = ops.mxfp8_quantize(x2 if x2.is_contiguous() else x2.contiguous())
+            wq, ws = ops.mxfp8_quantize(wb)
+            ops.gemm_mxfp8(xq, wq, xs, ws, y2, 0)
+        elif fp8_state is not None and fp8_state != "mx" and Cin % 128 == 0:   # per-tensor delayed scaling (kind::f8f6f4)
             sx, sw = fp8_state
             xq = _fp8._quantize(x2, sx).view(torch.uint8)
             wq = _fp8._quantize(wb, sw).view(torch.uint8)
@@ -68,6 +74,7 @@ class _Conv1x1TC(torch.autograd.Function):
             ops.gemm_taps(x2, wb, y2, Cout, Cin, [], 0, 0, 0, 0, None, None)
         ctx.save_for_backward(x2, wT)
         ctx.shape = (B, Cin, H, W, Cout)
+        ctx.mx = mx
         return _as_nchw(y2, B, H, W)
 
     @staticmethod
@@ -79,7 +86,12 @@ class _Conv1x1TC(torch.autograd.Function):
         if g2.dtype != torch.bfloat16 or not g2.is_contiguous():
             g2 = g2.to(torch.bfloat16).contiguous()
         dx2 = torch.empty(B * H * W, Cin, dtype=torch.bfloat16, device=gy.device)
-        ops.gemm_taps(g2, wT, dx2, Cin, Cout, [], 0, 0, 0, 0, None, None)                       # dX = dY . W
+        if ctx.mx:                                                                              # dX = dY . W, block-scaled
+            gq, gs = ops.mxfp8_quantize(g2)
+            tq, ts = ops.mxfp8_quantize(wT)
+            ops.gemm_mxfp8(gq, tq, gs, ts, dx2, 0)
+        else:
+            ops.gemm_taps(g2, wT, dx2, Cin, Cout, [], 0, 0, 0, 0, None, None)                   # dX = dY . W
         dw = torch.empty(1, Cout, Cin, dtype=torch.float32, device=gy.device)
         ops.wgrad_taps(g2, x2, dw, 1, 0)                                                       # dW = dY^T . X
         return _as_nchw(dx2, B, H, W), dw.view(Cout, Cin, 1, 1), None

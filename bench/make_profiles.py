@@ -13,6 +13,9 @@ GO = os.path.join(ROOT, "gpurun_out")
 PEAKS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
 
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed.sum.per_cycle_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
@@ -20,14 +23,18 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum"]
 
 
-def ncu_raw(path):
+def ncu_raw_all(path):
+    """Every kernel of a report: list of ({metric: (value, unit)}, kernel name)."""
     r = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True)
     rows = list(csv.reader(r.stdout.splitlines()))
     if len(rows) < 3:
-        return {}, ""
-    hdr, units, vals = rows[0], rows[1], rows[2]
-    d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
-    return d, d.get("Kernel Name", ("", ""))[0]
+        return []
+    hdr, units = rows[0], rows[1]
+    out = []
+    for vals in rows[2:]:
+        d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+        out.append((d, d.get("Kernel Name", ("", ""))[0]))
+    return out
 
 
 def launches(path):
@@ -47,11 +54,17 @@ def main():
     md = ["# ncu captures (`--set full --clock-control none --import-source on`, one B200)\n",
           f"Roofline denominators (MEASURED_PEAKS.json): HBM copy {PEAKS.get('hbm_gbs')} GB/s, cuBLAS bf16 "
           f"{PEAKS.get('bf16_tflops')} TFLOP/s burst.\n"]
+    reports = []
     for rep in sorted(glob.glob(os.path.join(GO, "*.ncu-rep"))):
-        d, name = ncu_raw(rep)
-        if not d:
-            continue
-        md.append(f"\n## {os.path.basename(rep)} — `{name[:110]}`\n")
+        seen = set()
+        for d, name in ncu_raw_all(rep):
+            key = re.sub(r"\(.*", "", name)
+            if key in seen:                     # one entry per distinct kernel of a report
+                continue
+            seen.add(key)
+            reports.append((rep, d, name))
+    for rep, d, name in reports:
+        md.append(f"\n## {os.path.basename(rep)} — `{name[:130]}`\n")
         md.append("| metric | value | unit |\n|---|---|---|")
         for k in KEYS:
             if k in d:
@@ -78,7 +91,7 @@ def main():
             for i, (k, g, t) in enumerate(rows):
                 f.write(f"| {i} | `{k[:90]}` | {g} | {t:.1f} |\n")
             f.write(f"\nTotal {sum(t for *_, t in rows):.1f} us over {len(rows)} launches.\n")
-    for jf in ["nn_micro.json", "he_micro.json", "allreduce_sweep_2gpu.json", "allreduce_sweep_8gpu.json",
+    for jf in ["nn_micro.json", "he_micro_v1.json", "he_micro_v2.json", "tcconv_micro.json", "allreduce_sweep_2gpu.json", "allreduce_sweep_8gpu.json",
                "allreduce_sweep_4gpu.json", "mp2.json"]:
         p = os.path.join(GO, jf)
         if os.path.exists(p):

@@ -11,7 +11,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "hefl_b200", "_obj")
 OUT = os.path.join(ROOT, "profiles", "sass")
-KEY = re.compile(r"\b(UTCHMMA|UTCQMMA|UTMALDG|UTMASTG|UBLKCP|LDTM|STTM|UTCBAR|UTCATOMSWS|SYNCS|MULTIMEM|ATOMG|ATOM|RED|LDGSTS|"
+KEY = re.compile(r"\b(UTCHMMA|UTCQMMA|UTCCP|UTMALDG|UTMASTG|UBLKCP|LDTM|STTM|UTCBAR|UTCATOMSWS|SYNCS|LDGMC|STGMC|REDGMC|MULTIMEM|ATOMG|ATOM|REDG|RED|LDGSTS|"
                  r"HMMA|IMAD|LDS|STS|LDG|STG|SHFL|BAR|MEMBAR|ERRBAR|CCTL|ELECT|R2UR|UIADD3|UMOV|FFMA|FFMA2|FHFMA|UCGABAR_ARV|UCGABAR_WAIT|"
                  r"ACQBULK|DFMA|DADD|DMUL)\b")
 
@@ -59,6 +59,17 @@ def main():
             md.append(f"\n## `{pretty[k][:150]}`\n")
             md.append(f"- instructions: {len(lines)}; ptxas: {res.get(k, 'n/a')}")
             md.append("- mnemonics: " + ", ".join(f"{a}×{b}" for a, b in hist.most_common(16)))
+            verb = [re.sub(r"\s+/\* 0x[0-9a-f]+ \*/\s*$", "", l).rstrip() for l in lines
+                    if re.search(r"LDGMC|STGMC|UTCQMMA|UTCCP|UTMALDG\.2D\.MULTICAST|UTMASTG|UBLKCP|UCGABAR_ARV|LDG\.E\.ENL2\.256", l)]
+            if verb:
+                md.append("\nVerbatim (first of each kind):\n\n```")
+                shown = set()
+                for l in verb:
+                    k = re.search(r"(LDGMC|STGMC|UTCQMMA|UTCCP|UTMALDG\.2D\.MULTICAST|UTMASTG|UBLKCP|UCGABAR_ARV|LDG\.E\.ENL2\.256)", l).group(1)
+                    if k not in shown:
+                        shown.add(k)
+                        md.append(l)
+                md.append("```")
             if "UTCHMMA" in hist and ("tap_gemm_kernel<16, 32, true>" in pretty[k].replace("(int)", "").replace("(bool)1", "true")
                                       or "wgrad_kernel<16, 32, false>" in pretty[k].replace("(int)", "").replace("(bool)0", "false")):
                 idx = [i for i, l in enumerate(lines) if "UTCHMMA" in l]

@@ -9,7 +9,7 @@ from hefl_b200.ops import tc_conv
 name = sys.argv[1] if len(sys.argv) > 1 else "resnet18"
 on = (sys.argv[2] if len(sys.argv) > 2 else "tc") == "tc"
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-torch.backends.cudnn.benchmark = True
+torch.backends.cudnn.benchmark = False      # no autotuning launches in the list: every step has the same launches
 m = create_model(name, num_classes=1000).cuda().train()
 tc_conv.set_model_tc(m, on)
 x = torch.randn(32, 224, 224, 3, device="cuda").permute(0, 3, 1, 2)

@@ -43,9 +43,12 @@ def test_three_epochs_of_the_bf16_engine_track_fp32_pytorch():
     # the first epoch is still in the smooth regime: the two must agree closely there. (Mid-training losses are
     # chaotic -- two fp32 runs of this test differ by 4 % in epoch 2 because of atomics ordering alone.)
     assert abs(h_e[0].loss - h_r[0].loss) <= 0.05 * h_r[0].loss
-    assert abs(h_e[0].accuracy - h_r[0].accuracy) <= 0.03
-    # measured on B200: losses (0.6454, 0.1647, 0.0000) vs fp32 (0.6498, 0.1791, 0.0000), accuracy 0.512 / 1.0 / 1.0
-    # on both; the trained weights stay close (bf16 activations, fp32 master weights and moments): cosine 0.9963
+    # epoch-1 accuracy is NOT compared tightly: at loss 0.65 the logits sit at the decision boundary and the running
+    # accuracy is a thresholded quantity (observed 0.512 vs 0.512 on one box, 0.574 vs 0.512 on another, with the
+    # losses 0.6457 / 0.6497 both times); it only has to be in the same regime
+    assert abs(h_e[0].accuracy - h_r[0].accuracy) <= 0.15
+    # measured on B200: losses (0.6454, 0.1647, 0.0000) vs fp32 (0.6498, 0.1791, 0.0000), accuracy 1.0 / 1.0 from
+    # epoch 2 on both; the trained weights stay close (bf16 activations, fp32 master weights and moments): cosine 0.9963
     cos = torch.nn.functional.cosine_similarity(pack_e.flat, pack_r.flat, dim=0).item()
     assert cos > 0.99
 
@@ -59,9 +62,11 @@ def test_graph_and_pipeline_path_equals_the_eager_path_over_eight_steps():
     assert int(a.step_t.item()) == int(b.step_t.item()) == 8
     # same kernels, same order of operations; only the fp32 atomics of the weight gradients reorder. Adam moves
     # every weight by ~lr per step whatever the size of its gradient, so a weight whose gradient is pure rounding
-    # noise may drift by up to steps * lr = 8e-3; the bulk must agree far better than that.
+    # noise may drift by up to steps * lr = 8e-3 in EACH run, in opposite directions in the worst case (observed
+    # maxima over boxes: 6.9e-3 ... 8.3e-3); the bulk must agree far better than that.
     d = (pack_a.flat - pack_b.flat).abs()
-    print("graph vs eager: max", float(d.max()), "mean", float(d.mean()))
-    assert float(d.max()) <= 8 * 1e-3 + 1e-4
+    print("graph vs eager: max", float(d.max()), "mean", float(d.mean()),
+          "share above 4e-3:", float((d > 4e-3).float().mean()))
+    assert float(d.max()) <= 2 * 8 * 1e-3
     assert float(d.mean()) < 6e-4
     assert torch.nn.functional.cosine_similarity(pack_a.flat, pack_b.flat, dim=0).item() > 0.9995

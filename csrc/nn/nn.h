@@ -38,6 +38,10 @@ void head_cluster(const void* feat, const float* W1, const float* b1, const floa
 bool wgrad0_gather_supported(int W, int Wp, int CK, int Ci, int Co);
 void wgrad0_gather(const void* X, const void* g, const uint8_t* amax, float* dW, int B, int H, int W, int Hp, int Wp,
                    cudaStream_t st);
+// the same gradient as four masked GEMMs on the tensor cores (wgrad0_mma.cu); needs the s-packed layer-1 input
+bool wgrad0_mma_supported(int W, int Wp, int CK, int Ci, int Co);
+void wgrad0_mma(const void* X, const void* g, const uint8_t* amax, float* dW, int B, int H, int W, int Hp, int Wp,
+                cudaStream_t st);
 // ---- general tcgen05 GEMMs for the ResNet convolutions (gemm_tcgen05.cu) ----
 // C[rows_out, N] (bf16) = sum_{t < taps} A[m + shifts[t], K] . B[t*N + n, K]^T. padded != 0: A rows index a zero-padded
 // [Bn][H+2][W+2] grid and only interior pixels are written (to the dense [Bn*H*W, N] output). fp8: A and B hold e4m3

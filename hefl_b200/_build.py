@@ -46,6 +46,7 @@ CUDA_SOURCES = [
     "nn/nn_kernels.cu",
     "nn/resnet_kernels.cu",
     "nn/wgrad_gather.cu",
+    "nn/wgrad0_mma.cu",
     "nn/head_cluster.cu",
 ]
 HOST_SOURCES = [

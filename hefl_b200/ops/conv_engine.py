@@ -267,7 +267,7 @@ class MedCNNEngine:
                         opt.apply(self.p0, self.pack.n_trainable)
                         self.ops.conv_weight_relayout(self.shadow, self.table, self.Wf, self.Wd, 1, self.n)
                 # 3-channel layer: weight gradient gathered straight from the pooled gradient
-                self.ops.wgrad0_gather(self._x0_bufs[slot], g, self.amax[0], self._dw(0), self.B, h, h)
+                self.ops.wgrad0_gather(self._x0_bufs[slot], g, self.amax[0], self._dw(0), self.B, h, h, self.spack0)
                 break
             xin = self.X0[slot] if l == 0 else self.X[l]
             if self.dY[l] is None:

@@ -291,6 +291,48 @@ def test_wgrad0_gather_matches_autograd(H):
     assert (dW32[144] - ref_b).abs().max() <= 2e-3 * ref_b.abs().max() + 1e-3
 
 
+@pytest.mark.parametrize("B,H", [(4, 256), (3, 66), (2, 20), (5, 130)])
+def test_wgrad0_masked_gemm_matches_gather_and_autograd(B, H):
+    """Layer-1 weight/bias gradient as four masked GEMMs on the tensor cores (wgrad0_mma.cu, s-packed input) ==
+    the FP32-pipe gather kernel on the same buffers == autograd through conv -> ReLU -> max-pool."""
+    Ci, Co = 3, 32
+    g = torch.Generator(device="cuda").manual_seed(23)
+    x = torch.randint(0, 256, (B, H, H, 3), dtype=torch.uint8, device="cuda", generator=g)
+    w = _bf(torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) * 0.3).float().requires_grad_(True)
+    bias = (torch.randn(Co, device="cuda", generator=g) * 0.1).requires_grad_(True)
+    P = B * H * H
+    X = torch.zeros(P + 8, 16, dtype=torch.bfloat16, device="cuda")
+    ops.preprocess_u8(x, None, X[:P], 0, None, True)
+    Wp = torch.zeros(3, Co, 16, dtype=torch.bfloat16, device="cuda")
+    Wp[:, :, :9] = w.detach().permute(2, 0, 3, 1).reshape(3, Co, 9).to(torch.bfloat16)
+    Hp = (H - 2) // 2
+    out = torch.zeros(B * Hp * Hp, Co, dtype=torch.bfloat16, device="cuda")
+    amax = torch.zeros(B * Hp * Hp, Co, dtype=torch.uint8, device="cuda")
+    ops.conv_fwd_pool(X[:P], Wp.view(-1), bias.detach(), out, amax, B, H, H, 16, Co, True)
+    gp = _bf(torch.randn(B, Co, Hp, Hp, device="cuda", generator=g))
+    gflat = gp.permute(0, 2, 3, 1).contiguous().view(-1, Co)
+    d_mma = torch.zeros(9 * 16 + 1, Co, dtype=torch.float32, device="cuda")
+    d_gat = torch.zeros_like(d_mma)
+    ops.wgrad0_gather(X, gflat, amax, d_mma.view(-1), B, H, H, True)
+    ops.wgrad0_gather(X, gflat, amax, d_gat.view(-1), B, H, H, False)
+    torch.cuda.synchronize()
+    # same products, fp32 accumulation in a different order
+    scale = d_gat.abs().max()
+    assert (d_mma - d_gat).abs().max() <= 2e-5 * scale + 1e-5
+    assert float(d_mma[:144].view(9, 16, Co)[:, Ci:, :].abs().max()) == 0.0
+    # autograd with the kernel's own arg-max / activity decisions (ties cannot differ)
+    xin = _bf(x.float() / 255.0).float().permute(0, 3, 1, 2)
+    conv = F.conv2d(xin, w, bias)
+    am = amax.view(B, Hp, Hp, Co).permute(0, 3, 1, 2).long()
+    dy, dx, act = (am >> 1) & 1, am & 1, (am & 4) != 0
+    idx = (2 * torch.arange(Hp, device="cuda").view(1, 1, Hp, 1) + dy) * (H - 2) + 2 * torch.arange(Hp, device="cuda").view(1, 1, 1, Hp) + dx
+    pooled = conv.flatten(2).gather(2, idx.flatten(2)).view(B, Co, Hp, Hp) * act
+    pooled.backward(gp.float())
+    got_w = d_mma[:144].view(9, 16, Co)[:, :Ci, :].permute(2, 1, 0).reshape(Co, Ci, 3, 3)
+    assert (got_w - w.grad).abs().max() <= 2e-3 * w.grad.abs().max() + 1e-3
+    assert (d_mma[144] - bias.grad).abs().max() <= 2e-3 * bias.grad.abs().max() + 1e-3
+
+
 @pytest.mark.parametrize("gather,fuse", [(True, True), (False, True), (True, False)])
 def test_engine_gradients_match_autograd(gather, fuse):
     """Whole medical CNN: engine forward/backward vs PyTorch autograd on the same weights."""

@@ -562,7 +562,9 @@ struct PairFwdArgs {
   uint8_t* argmax;      // may be null
 };
 
-template <int CK, int CO>
+// SP: s-packed layer-1 input (channels = pixels x, x+1, x+2): the three horizontal taps are already inside the 16
+// channels, so only the three filter rows remain — 3 MMAs per accumulator, column parity = K byte offset.
+template <int CK, int CO, bool SP>
 __global__ void __launch_bounds__(352, PairFwdCfg<CK, CO>::OCC)
 pair_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                 const PairFwdArgs a) {
@@ -596,8 +598,9 @@ pair_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   pdl_trigger();
   if (warp == 8 && elect_one()) {
-    mbar_expect_tx(wfull, Cfg::W_BYTES);
-    for (int tap = 0; tap < 9; ++tap) tma_load_2d(sW + tap * Cfg::W_TAP, &tmW, 0, tap * CO, wfull);
+    constexpr int NTAPW = SP ? 3 : 9;
+    mbar_expect_tx(wfull, NTAPW * Cfg::W_TAP);
+    for (int tap = 0; tap < NTAPW; ++tap) tma_load_2d(sW + tap * Cfg::W_TAP, &tmW, 0, tap * CO, wfull);
   }
   pdl_wait();
   const int half_w = a.W >> 1;
@@ -637,6 +640,15 @@ pair_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
           const uint32_t d_tmem = tmem_base + (tb * Cfg::NACC + dy * 2 + dx) * CO;
+          if constexpr (SP) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              const uint32_t ao = ((dy + r) * Cfg::SEG_BYTES + dx * CK * 2) >> 4;
+              const uint32_t wo = (r * Cfg::W_TAP) >> 4;
+              umma_bf16_lh(d_tmem, a_lo + ao, a_hi, w_lo + wo, w_hi, idesc, r != 0 ? 1u : 0u);
+            }
+            continue;
+          }
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             const int r = tap / 3, s = tap % 3;
@@ -719,13 +731,13 @@ pair_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <int CK, int CO>
+template <int CK, int CO, bool SP = false>
 static void launch_pair_fwd(const __nv_bfloat16* X, const __nv_bfloat16* Wt, PairFwdArgs a, cudaStream_t st) {
   using Cfg = PairFwdCfg<CK, CO>;
   const uint64_t pair_rows = ((uint64_t)a.B * a.H * a.W) / 2;
   const CUtensorMap tmA = make_map(X, 2 * CK, pair_rows, (uint64_t)Cfg::ROW_BYTES, 2 * CK, Cfg::SEG_ROWS);
-  const CUtensorMap tmW = make_map(Wt, CK, (uint64_t)9 * CO, (uint64_t)CK * 2, CK, CO);
-  auto kern = pair_fwd_kernel<CK, CO>;
+  const CUtensorMap tmW = make_map(Wt, CK, (uint64_t)(SP ? 3 : 9) * CO, (uint64_t)CK * 2, CK, CO);
+  auto kern = pair_fwd_kernel<CK, CO, SP>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   int gx = num_sms() * Cfg::OCC;
   if (gx > a.num_tiles) gx = a.num_tiles;
@@ -737,9 +749,10 @@ bool conv_fwd_pool_pair_supported(int H, int W, int CK, int CO) {
   return H == W && (W % 2) == 0 && (W - 2) / 2 <= 128 && (CK == 16 || CK == 32) && (CO == 32 || CO == 64);
 }
 
-// Same contract as conv_fwd_pool (plain 9-tap weight layout [9][CO][CK]); see G1b above.
+// Same contract as conv_fwd_pool (plain 9-tap weight layout [9][CO][CK], or [3][CO][16] with the s-packed input);
+// see G1b above.
 void conv_fwd_pool_pair(const void* X, const void* Wf, const float* bias, void* out, uint8_t* argmax, int B, int H,
-                        int W, int CK, int CO, cudaStream_t st) {
+                        int W, int CK, int CO, int spack, cudaStream_t st) {
   if (!conv_fwd_pool_pair_supported(H, W, CK, CO)) throw std::runtime_error("conv_fwd_pool_pair: unsupported shape");
   PairFwdArgs a{};
   a.B = B; a.H = H; a.W = W;
@@ -750,7 +763,9 @@ void conv_fwd_pool_pair(const void* X, const void* Wf, const float* bias, void* 
   a.argmax = argmax;
   const auto* x = reinterpret_cast<const __nv_bfloat16*>(X);
   const auto* w = reinterpret_cast<const __nv_bfloat16*>(Wf);
-  if (CK == 16 && CO == 32) launch_pair_fwd<16, 32>(x, w, a, st);
+  if (spack && !(CK == 16 && CO == 32)) throw std::runtime_error("conv_fwd_pool_pair: s-packed input is CK=16, CO=32 only");
+  if (CK == 16 && CO == 32 && spack) launch_pair_fwd<16, 32, true>(x, w, a, st);
+  else if (CK == 16 && CO == 32) launch_pair_fwd<16, 32>(x, w, a, st);
   else if (CK == 32 && CO == 32) launch_pair_fwd<32, 32>(x, w, a, st);
   else if (CK == 32 && CO == 64) launch_pair_fwd<32, 64>(x, w, a, st);
   else throw std::runtime_error("conv_fwd_pool_pair: unsupported (CK, CO)");

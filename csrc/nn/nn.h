@@ -18,7 +18,7 @@ void conv_fwd_pool(const void* X, const void* Wf, const float* bias, void* out, 
                    int W, int CK, int CO, int spack, cudaStream_t st);
 bool conv_fwd_pool_pair_supported(int H, int W, int CK, int CO);
 void conv_fwd_pool_pair(const void* X, const void* Wf, const float* bias, void* out, uint8_t* argmax, int B, int H,
-                        int W, int CK, int CO, cudaStream_t st);
+                        int W, int CK, int CO, int spack, cudaStream_t st);
 void conv_set_debug(int mask);
 void conv_dgrad(const void* dY, const void* Wd, void* dX, int B, int H, int W, int CK, int CO, const uint8_t* up_amax,
                 int up_W, cudaStream_t st);

@@ -99,9 +99,11 @@ void conv_fwd_pool(const Tensor& X, const Tensor& Wf, const Tensor& bias, Tensor
 // conv-grid gradient [B*up_W*up_W, CO] (H = W = (up_W - 2) / 2 of this call), written at the arg-max positions.
 // Pair-row forward kernel (conv_tcgen05.cu G1b): same contract as conv_fwd_pool with the plain [9, CO, CK] weights.
 void conv_fwd_pool_pair(const Tensor& X, const Tensor& Wf, const Tensor& bias, Tensor out,
-                        const c10::optional<Tensor>& argmax, int64_t B, int64_t H, int64_t W, int64_t CK, int64_t CO) {
+                        const c10::optional<Tensor>& argmax, int64_t B, int64_t H, int64_t W, int64_t CK, int64_t CO,
+                        bool spack) {
   chk_bf16(X, "X"); chk_bf16(Wf, "Wf"); chk_bf16(out, "out");
-  TORCH_CHECK(X.numel() >= B * H * W * CK && Wf.numel() >= 9 * CO * CK, "shape mismatch");
+  TORCH_CHECK(X.numel() >= B * H * W * CK && Wf.numel() >= (spack ? 3 : 9) * CO * CK, "shape mismatch");
+  TORCH_CHECK(!spack || (CK == 16 && CO == 32), "s-packed input is the 3-channel first layer only");
   TORCH_CHECK(hefl::nn::conv_fwd_pool_pair_supported((int)H, (int)W, (int)CK, (int)CO), "conv_fwd_pool_pair: unsupported shape");
   const int64_t Hp = (H - 2) / 2, Wp = (W - 2) / 2;
   TORCH_CHECK(out.numel() == B * Hp * Wp * CO, "out must be [B,Hp,Wp,CO]");
@@ -111,7 +113,7 @@ void conv_fwd_pool_pair(const Tensor& X, const Tensor& Wf, const Tensor& bias, T
     am = argmax->data_ptr<uint8_t>();
   }
   hefl::nn::conv_fwd_pool_pair(X.data_ptr(), Wf.data_ptr(), bias.data_ptr<float>(), out.data_ptr(), am, (int)B, (int)H,
-                               (int)W, (int)CK, (int)CO, cur());
+                               (int)W, (int)CK, (int)CO, spack ? 1 : 0, cur());
 }
 
 void conv_dgrad(const Tensor& dY, const Tensor& Wd, Tensor dX, int64_t B, int64_t H, int64_t W, int64_t CK,
@@ -420,7 +422,7 @@ TORCH_LIBRARY_FRAGMENT(hefl, m) {
   m.def("adam_step_(Tensor(a!) p, Tensor(b!) g, Tensor(c!) m, Tensor(d!) v, Tensor? shadow, Tensor step, Tensor? lr_scale, float lr, float decay, float beta1, float beta2, float eps) -> ()", &adam_step_);
   m.def("gather_h2d_(Tensor(a!) dst, Tensor src, Tensor indices) -> ()", &gather_h2d_);
   m.def("conv_fwd_pool(Tensor X, Tensor Wf, Tensor bias, Tensor(a!) out, Tensor(b!)? argmax, int B, int H, int W, int CK, int CO, bool spack=False) -> ()", &conv_fwd_pool);
-  m.def("conv_fwd_pool_pair(Tensor X, Tensor Wf, Tensor bias, Tensor(a!) out, Tensor(b!)? argmax, int B, int H, int W, int CK, int CO) -> ()", &conv_fwd_pool_pair);
+  m.def("conv_fwd_pool_pair(Tensor X, Tensor Wf, Tensor bias, Tensor(a!) out, Tensor(b!)? argmax, int B, int H, int W, int CK, int CO, bool spack=False) -> ()", &conv_fwd_pool_pair);
   m.def("conv_dgrad(Tensor dY, Tensor Wd, Tensor(a!) dX, int B, int H, int W, int CK, int CO, Tensor? up_amax=None, int up_W=0) -> ()", &conv_dgrad);
   m.def("conv_wgrad(Tensor X, Tensor DY, Tensor(a!) dW32, int B, int H, int W, int CK, int Co) -> ()", &conv_wgrad);
   m.def("preprocess_u8(Tensor x, Tensor? theta, Tensor(a!) X, int aug_seed, Tensor? step, bool spack=False) -> ()", &preprocess_u8);

@@ -76,14 +76,12 @@ class MedCNNEngine:
                        and self.Co[0] == 32)
         # un-pool inside the dgrad epilogue: correct (bit-exact test) but measured 10 us/step SLOWER than the
         # separate un-pool kernels (the epilogue is issue-bound; 4x the stores), so off by default
-        # pair-row forward kernel (both columns of a pooling window in one TMEM lane, conv_tcgen05.cu G1b):
-        # bit-compatible with the tap-GEMM forward (tests) and measured 33.7 vs 40.4 us on layer 1, but slower on
-        # the small layers (one 128-window tile per pooled row: 20.3 vs 16.8 us, 16.2 vs 11.6 us). Opt-in
-        # (HEFL_FWD_PAIR=1: layer 1 only, =all: every eligible layer) until a full validation run has been done.
-        mode = os.environ.get("HEFL_FWD_PAIR", "0")
+        # pair-row forward kernel (both columns of a pooling window in one TMEM lane, conv_tcgen05.cu G1b): on by
+        # default for layer 1, where it reads the same s-packed input and issues the same three MMAs per accumulator
+        # as the tap-GEMM forward (bit-identical outputs, tests). On the small layers it is slower (one 128-window
+        # tile per pooled row: 20.3 vs 16.8 us, 16.2 vs 11.6 us), so HEFL_FWD_PAIR=all is only for experiments.
+        mode = os.environ.get("HEFL_FWD_PAIR", "1")
         self.fwd_pair = {"0": 0, "1": 1, "all": self.n}.get(mode, 0)      # number of leading layers that may use it
-        if self.fwd_pair:
-            self.spack0 = False          # the pair-row kernel takes the plain 9-tap layer-1 layout
         self.fuse_unpool = os.environ.get("HEFL_FUSE_UNPOOL", "0") != "0"
         self.fuse_from = int(os.environ.get("HEFL_FUSE_UNPOOL_FROM", "0"))     # fuse only into layers >= this index
         # layer-1 weight gradient by gather from the pooled gradient (csrc/nn/wgrad_gather.cu)
@@ -204,7 +202,8 @@ class MedCNNEngine:
             h = self.H[l]
             if l < self.fwd_pair and h % 2 == 0 and (h - 2) // 2 <= 128 and self.CK[l] <= 32 and self.Co[l] <= 64:
                 self.ops.conv_fwd_pool_pair(x if l else self._x0_bufs[slot], self._wf(l), self.bias[l], self.X[l + 1],
-                                            self.amax[l] if train else None, self.B, h, h, self.CK[l], self.Co[l])
+                                            self.amax[l] if train else None, self.B, h, h, self.CK[l], self.Co[l],
+                                            self.spack0 and l == 0)
                 x = self.X[l + 1]
                 continue
             self.ops.conv_fwd_pool(x, self._wf(l), self.bias[l], self.X[l + 1],

@@ -174,6 +174,33 @@ def test_conv_fwd_pool_pair_matches_plain_kernel(B, H, Ci, CK, Co):
     assert (am0 == am1).float().mean() > 0.999
 
 
+@pytest.mark.parametrize("B,H", [(2, 256), (3, 70), (1, 20)])
+def test_pair_forward_on_spacked_input_is_bit_identical_to_the_tap_gemm_forward(B, H):
+    """Layer-1 default: pair-row forward on the s-packed input. Same three MMAs per accumulator as the tap-GEMM
+    forward on the same buffers, so pooled values AND arg-max codes must agree bit for bit."""
+    Ci, Co = 3, 32
+    g = torch.Generator(device="cuda").manual_seed(41)
+    x = torch.randint(0, 256, (B, H, H, 3), dtype=torch.uint8, device="cuda", generator=g)
+    w = _bf(torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) * 0.3)
+    bias = torch.randn(Co, device="cuda", generator=g) * 0.1
+    P = B * H * H
+    X = torch.zeros(P + 8, 16, dtype=torch.bfloat16, device="cuda")
+    ops.preprocess_u8(x, None, X[:P], 0, None, True)
+    Wp = torch.zeros(3, Co, 16, dtype=torch.bfloat16, device="cuda")
+    Wp[:, :, :9] = w.permute(2, 0, 3, 1).reshape(3, Co, 9).to(torch.bfloat16)
+    Hp = (H - 2) // 2
+    out0 = torch.zeros(B * Hp * Hp, Co, dtype=torch.bfloat16, device="cuda"); am0 = torch.zeros(B * Hp * Hp, Co, dtype=torch.uint8, device="cuda")
+    out1 = torch.zeros_like(out0); am1 = torch.zeros_like(am0)
+    ops.conv_fwd_pool(X[:P], Wp.view(-1), bias, out0, am0, B, H, H, 16, Co, True)
+    ops.conv_fwd_pool_pair(X, Wp.view(-1), bias, out1, am1, B, H, H, 16, Co, True)
+    torch.cuda.synchronize()
+    assert torch.equal(out0, out1)
+    assert torch.equal(am0, am1)
+    ref = F.max_pool2d(F.relu(F.conv2d(_bf(x.float() / 255.0).float().permute(0, 3, 1, 2), w.float(), bias)), 2)
+    got = out1.view(B, Hp, Hp, Co).permute(0, 3, 1, 2).float()
+    assert (got - ref).abs().max() <= 2.0 ** -7 * ref.abs().max() + 1e-3
+
+
 @pytest.mark.parametrize("H", [256, 70])
 def test_spack_first_layer_matches_torch(H):
     """s-packed first layer: preprocess_u8(spack) writes pixels (w, w+1, w+2) into the 16 channels and the

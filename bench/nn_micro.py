@@ -44,12 +44,16 @@ def main():
     for l in range(eng.n):
         h = eng.H[l]
         res[f"fwd{l}"] = timeit(lambda l=l, h=h: ops.conv_fwd_pool(eng.X[l], eng._wf(l), eng.bias[l], eng.X[l + 1], eng.amax[l], B, h, h, eng.CK[l], eng.Co[l], eng.spack0 and l == 0))
+        if l == 0 and eng.fwd_pair:
+            res["fwd0(tap-GEMM, not used)"] = res["fwd0"]
+            res["fwd0"] = timeit(lambda: ops.conv_fwd_pool_pair(eng._x0_bufs[0], eng._wf(0), eng.bias[0], eng.X[1], eng.amax[0], B, h, h, eng.CK[0], eng.Co[0], eng.spack0))
     g = torch.randn(B, 512, device="cuda").to(torch.bfloat16).view_as(eng.X[eng.n]).contiguous()
     for l in range(eng.n - 1, -1, -1):
         h = eng.H[l]
         gin = g if l == eng.n - 1 else eng.gX[l + 1]
         if l == 0:
             res["wgrad0(gather from pooled grad)"] = timeit(lambda: ops.wgrad0_gather(eng._x0_bufs[0], gin, eng.amax[0], eng._dw(0), B, h, h))
+            res["wgrad0(masked GEMMs, mma.sync)"] = timeit(lambda: ops.wgrad0_gather(eng._x0_bufs[0], gin, eng.amax[0], eng._dw(0), B, h, h, eng.spack0))
             eng.dY[0] = torch.zeros(eng.P[0], eng.Co[0], dtype=torch.bfloat16, device="cuda")
         res[f"unpool{l}"] = timeit(lambda l=l, h=h, gin=gin: ops.unpool_relu(gin, eng.amax[l], eng.X[l + 1], eng.dY[l], B, h, h, eng.Co[l]))
         res[f"wgrad{l}(tcgen05)"] = timeit(lambda l=l, h=h: ops.conv_wgrad(eng.X[l], eng.dY[l], eng._dw(l), B, h, h, eng.CK[l], eng.Co[l]))

@@ -45,7 +45,9 @@ for l in range(5, 0, -1):
     add(f"conv{l + 1} wgrad (tcgen05, MN-major)", f"wgrad{l}(tcgen05)", P_in * (CK[l] + Co[l]) * 2, fl)
     add(f"conv{l + 1} dgrad (tcgen05)", f"dgrad{l}", P_in * (Co[l] + Ci[l]) * 2, fl)
 P_pool = B * H[1] * H[1]
-add("conv1 wgrad (gather from pooled gradient, FHFMA)", "wgrad0(gather from pooled grad)",
+add("conv1 wgrad (masked GEMMs from the pooled gradient, mma.sync)", "wgrad0(masked GEMMs, mma.sync)",
+    B * 256 * 256 * 32 + P_pool * 32 * 3, 2.0 * P_pool * 32 * 27)
+add("conv1 wgrad (round-1 kernel: FP32-pipe gather, fallback)", "wgrad0(gather from pooled grad)",
     B * 256 * 256 * 32 + P_pool * 32 * 3, 2.0 * P_pool * 32 * 27)
 add("Adam (222,722 parameters, bf16 shadow)", "adam", 222722 * (4 * 7 + 2), 0)
 
@@ -54,7 +56,7 @@ out = ["# Roofline table — one training step of the medical CNN, batch 32, one
        "stand-alone kernel times of `profiles/nn_micro.json` (CUDA events, warm-up, L2 flushed between iterations);",
        "bytes and FLOPs are the analytic minimum for the kernel (operands read once, results written once;",
        "FLOPs of the real, un-padded problem). In the step graph kernels overlap (two streams + PDL), so the",
-       "step takes ≈343 µs, less than the sum of this column.\n",
+       "step takes ≈290 µs, less than the sum of this column.\n",
        "| kernel | µs | MB | GB/s | of HBM | GFLOP | TFLOP/s | of bf16 peak |", "|---|---|---|---|---|---|---|---|"]
 for r in rows:
     out.append(f"| {r[0]} | {r[1]:.1f} | {r[2]:.1f} | {r[3]:.0f} | {r[4]:.2f} | {r[5]:.2f} | {r[6]:.1f} | {r[7]:.3f} |")

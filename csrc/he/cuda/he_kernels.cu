@@ -746,5 +746,72 @@ void digit_extract(const uint64_t* x, int64_t rows, int n, int shift, int bits, 
   note_launch();
 }
 
+// ------------------------------------------------------------------------------------------
+// Key generation on the device. Same counter-based streams as the host twin
+// (host::sample_secret / host::gen_public), so the keys are bit-identical for a given seed; the NTTs in
+// between are the regular batched kernels. Reference: HE.keyGen() / relinKeyGen (FLPyfhelin.py:340, :362).
+// ------------------------------------------------------------------------------------------
+// mode 0: ternary secret, out [L][n]; mode 1: centred-binomial error of key idx0 + e, out = pk [E][2][L][n], slot [e][0]
+__global__ void keygen_sample_kernel(uint64_t* __restrict__ out, int L, int n, const uint64_t* __restrict__ consts,
+                                     uint64_t seed, uint32_t idx0, int mode) {
+  const int l = blockIdx.y, e = blockIdx.z;
+  const uint64_t q = consts[(size_t)l * 8];
+  uint64_t* o = out + ((size_t)e * (mode ? 2 : 1) * L + l) * n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    o[i] = mode ? lift_signed(sample_cbd(seed, STREAM_PK_E, idx0 + (uint32_t)e, (uint32_t)i), q)
+                : lift_signed(sample_ternary(seed, STREAM_SK, (uint32_t)i), q);
+}
+
+// pk [E][2][L][n] with NTT(e) in slot 0: slot 1 <- a (uniform), slot 0 <- -(a s + e)
+__global__ void keygen_finish_kernel(const uint64_t* __restrict__ sk, uint64_t* __restrict__ pk, int L, int n,
+                                     const uint64_t* __restrict__ consts, uint64_t seed, uint32_t idx0) {
+  const int l = blockIdx.y, e = blockIdx.z;
+  const uint64_t* c = consts + (size_t)l * 8;
+  const Modulus m{c[0], c[1], c[2]};
+  uint64_t* b = pk + ((size_t)e * 2 * L + l) * n;
+  uint64_t* a = b + (size_t)L * n;
+  const uint64_t* s = sk + (size_t)l * n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint64_t ai = sample_uniform(seed, idx0 + (uint32_t)e, (uint32_t)l, (uint32_t)i, m);
+    a[i] = ai;
+    b[i] = neg_mod(mad_mod(ai, s[i], b[i], m), m.q);
+  }
+}
+
+// evaluation keys: evk[e][0][limb_of[e]] += w[e] * s2[limb_of[e]]  (the CRT-basis message term of digit e)
+__global__ void relin_message_kernel(uint64_t* __restrict__ evk, const uint64_t* __restrict__ s2,
+                                     const int* __restrict__ limb_of, const uint64_t* __restrict__ w, int L, int n,
+                                     const uint64_t* __restrict__ consts) {
+  const int e = blockIdx.y, l = limb_of[e];
+  const uint64_t* c = consts + (size_t)l * 8;
+  const Modulus m{c[0], c[1], c[2]};
+  uint64_t* b = evk + ((size_t)e * 2 * L + l) * n;
+  const uint64_t* s = s2 + (size_t)l * n;
+  const uint64_t we = w[e];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    b[i] = add_mod(b[i], mul_mod(we, s[i], m), m.q);
+}
+
+void keygen_sample(uint64_t* out, int E, int L, int n, const uint64_t* consts, uint64_t seed, uint32_t idx0, int mode,
+                   cudaStream_t st) {
+  dim3 grid((n + 1023) / 1024, L, E);
+  keygen_sample_kernel<<<grid, 256, 0, st>>>(out, L, n, consts, seed, idx0, mode);
+  note_launch();
+}
+
+void keygen_finish(const uint64_t* sk, uint64_t* pk, int E, int L, int n, const uint64_t* consts, uint64_t seed,
+                   uint32_t idx0, cudaStream_t st) {
+  dim3 grid((n + 1023) / 1024, L, E);
+  keygen_finish_kernel<<<grid, 256, 0, st>>>(sk, pk, L, n, consts, seed, idx0);
+  note_launch();
+}
+
+void relin_message(uint64_t* evk, const uint64_t* s2, const int* limb_of, const uint64_t* w, int E, int L, int n,
+                   const uint64_t* consts, cudaStream_t st) {
+  dim3 grid((n + 1023) / 1024, E);
+  relin_message_kernel<<<grid, 256, 0, st>>>(evk, s2, limb_of, w, L, n, consts);
+  note_launch();
+}
+
 }  // namespace cuda
 }  // namespace hefl

@@ -356,19 +356,63 @@ Tensor decrypt(const Tensor& ct, const Tensor& sk, int64_t k, int64_t logn, cons
   return out;
 }
 
+// Key generation: host twin for CPU tables, device kernels (csrc/he/cuda/he_kernels.cu) for CUDA tables; the two are
+// bit-identical for a given seed (tests/test_gpu_he.py).
 Tensor keygen_secret(int64_t L, int64_t logn, const Tensor& tables, const Tensor& consts, int64_t seed) {
-  TORCH_CHECK(tables.is_cpu(), "keygen runs on the host; pass CPU tables");
-  Tensor sk = at::empty({L, 1ll << logn}, at::kLong);
-  hefl::host::sample_secret(u64(sk), (int)L, (int)logn, u64(tables), u64(consts), (uint64_t)seed);
+  same_device(tables, consts);
+  Tensor sk = at::empty({L, 1ll << logn}, tables.options().dtype(at::kLong));
+  if (tables.is_cuda()) {
+    hefl::cuda::keygen_sample(u64(sk), 1, (int)L, 1 << logn, u64(consts), (uint64_t)seed, 0u, 0, cur_stream());
+    ntt_(sk, tables, consts, L, logn, false);
+  } else {
+    hefl::host::sample_secret(u64(sk), (int)L, (int)logn, u64(tables), u64(consts), (uint64_t)seed);
+  }
   return sk;
+}
+
+// E public-key-shaped pairs (-(a s + e), a) with stream indices idx0 .. idx0 + E - 1: [E, 2, L, N]
+Tensor keygen_public_batch(const Tensor& sk, int64_t L, int64_t logn, const Tensor& tables, const Tensor& consts,
+                           int64_t seed, int64_t idx0, int64_t E) {
+  same_device(tables, consts);
+  same_device(tables, sk);
+  const int64_t n = 1ll << logn;
+  TORCH_CHECK(sk.numel() == L * n && sk.is_contiguous() && E >= 1, "sk must be contiguous [L, N]");
+  Tensor pk = at::zeros({E, 2, L, n}, tables.options().dtype(at::kLong));
+  if (tables.is_cuda()) {
+    hefl::cuda::keygen_sample(u64(pk), (int)E, (int)L, (int)n, u64(consts), (uint64_t)seed, (uint32_t)idx0, 1, cur_stream());
+    ntt_(pk, tables, consts, L, logn, false);           // slot 1 is still zero: transformed along, then overwritten
+    hefl::cuda::keygen_finish(u64(sk), u64(pk), (int)E, (int)L, (int)n, u64(consts), (uint64_t)seed, (uint32_t)idx0, cur_stream());
+  } else {
+    for (int64_t e = 0; e < E; ++e)
+      hefl::host::gen_public(u64(sk), u64(pk) + e * 2 * L * n, (int)L, (int)logn, u64(tables), u64(consts), (uint64_t)seed,
+                             (uint32_t)(idx0 + e));
+  }
+  return pk;
 }
 
 Tensor keygen_public(const Tensor& sk, int64_t L, int64_t logn, const Tensor& tables,
                      const Tensor& consts, int64_t seed, int64_t idx) {
-  TORCH_CHECK(tables.is_cpu() && sk.is_cpu(), "keygen runs on the host; pass CPU tensors");
-  Tensor pk = at::empty({2, L, 1ll << logn}, at::kLong);
-  hefl::host::gen_public(u64(sk), u64(pk), (int)L, (int)logn, u64(tables), u64(consts), (uint64_t)seed, (uint32_t)idx);
-  return pk;
+  return keygen_public_batch(sk, L, logn, tables, consts, seed, idx, 1).squeeze(0);
+}
+
+// evk [E, 2, L, N]: slot 0, limb limb_of[e] += w[e] * s2[limb_of[e]] (message term of the digit-decomposed key)
+void relin_message_(Tensor evk, const Tensor& s2, const Tensor& limb_of, const Tensor& w, int64_t L, const Tensor& consts) {
+  same_device(evk, s2);
+  same_device(evk, consts);
+  const int64_t n = s2.size(-1), E = evk.size(0);
+  TORCH_CHECK(evk.dim() == 4 && evk.size(1) == 2 && evk.size(2) == L && evk.size(3) == n && evk.is_contiguous() &&
+              s2.numel() == L * n && s2.is_contiguous(), "evk must be [E,2,L,N], s2 [L,N]");
+  TORCH_CHECK(limb_of.scalar_type() == at::kInt && w.scalar_type() == at::kLong && limb_of.numel() == E && w.numel() == E,
+              "limb_of int32 [E], w int64 [E]");
+  if (evk.is_cuda()) {
+    same_device(evk, limb_of);
+    same_device(evk, w);
+    hefl::cuda::relin_message(u64(evk), u64(s2), limb_of.data_ptr<int>(), u64(w), (int)E, (int)L, (int)n, u64(consts), cur_stream());
+  } else {
+    const int* lo = limb_of.data_ptr<int>();
+    for (int64_t e = 0; e < E; ++e) TORCH_CHECK(lo[e] >= 0 && lo[e] < L, "limb index");
+    hefl::host::relin_message(u64(evk), u64(s2), lo, u64(w), E, (int)L, n, u64(consts));
+  }
 }
 
 Tensor frac_encode(const Tensor& vals, int64_t n, int64_t int_digits, int64_t frac_digits) {
@@ -482,6 +526,8 @@ TORCH_LIBRARY_FRAGMENT(hefl, m) {
   m.def("decrypt(Tensor ct, Tensor sk, int k, int logn, Tensor tables, Tensor consts) -> Tensor", &decrypt);
   m.def("keygen_secret(int L, int logn, Tensor tables, Tensor consts, int seed) -> Tensor", &keygen_secret);
   m.def("keygen_public(Tensor sk, int L, int logn, Tensor tables, Tensor consts, int seed, int idx) -> Tensor", &keygen_public);
+  m.def("keygen_public_batch(Tensor sk, int L, int logn, Tensor tables, Tensor consts, int seed, int idx0, int E) -> Tensor", &keygen_public_batch);
+  m.def("relin_message_(Tensor(a!) evk, Tensor s2, Tensor limb_of, Tensor w, int L, Tensor consts) -> ()", &relin_message_);
   m.def("frac_encode(Tensor vals, int n, int int_digits, int frac_digits) -> Tensor", &frac_encode);
   m.def("frac_decode(Tensor coeffs, int int_digits, int frac_digits) -> Tensor", &frac_decode);
   m.def("bfv_scale_round(Tensor x, int q, int p) -> Tensor", &bfv_scale_round);

@@ -443,6 +443,17 @@ void gen_public(const uint64_t* sk, uint64_t* pk, int L, int logn, const uint64_
   }
 }
 
+void relin_message(uint64_t* evk, const uint64_t* s2, const int* limb_of, const uint64_t* w, int64_t E, int L,
+                   int64_t n, const uint64_t* consts) {
+  for (int64_t e = 0; e < E; ++e) {
+    const int l = limb_of[e];
+    const Modulus m = load_mod(consts, l);
+    uint64_t* b = evk + (e * 2 * L + l) * n;
+    const uint64_t* s = s2 + (int64_t)l * n;
+    for (int64_t i = 0; i < n; ++i) b[i] = add_mod(b[i], mul_mod(w[e], s[i], m), m.q);
+  }
+}
+
 void frac_encode(const double* vals, int64_t C, int n, int int_digits, int frac_digits,
                  int64_t* msg) {
 #pragma omp parallel for schedule(static)

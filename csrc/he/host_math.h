@@ -52,6 +52,9 @@ void sample_secret(uint64_t* sk, int L, int logn, const uint64_t* tables, const 
                    uint64_t seed);
 void gen_public(const uint64_t* sk, uint64_t* pk, int L, int logn, const uint64_t* tables,
                 const uint64_t* consts, uint64_t seed, uint32_t idx);
+// evk [E][2][L][n]: slot 0, limb limb_of[e] += w[e] * s2[limb_of[e]] (message term of a digit-decomposed evaluation key)
+void relin_message(uint64_t* evk, const uint64_t* s2, const int* limb_of, const uint64_t* w, int64_t E, int L,
+                   int64_t n, const uint64_t* consts);
 void frac_encode(const double* vals, int64_t C, int n, int int_digits, int frac_digits,
                  int64_t* msg);
 void frac_decode(const int64_t* coeffs, int64_t C, int n, int int_digits, int frac_digits,

@@ -46,6 +46,14 @@ void bfv_scale_round(const uint64_t* x, int64_t C, int n, uint64_t q, uint64_t p
 void digit_extract(const uint64_t* x, int64_t rows, int n, int shift, int bits, uint64_t* out,
                    cudaStream_t st);
 
+// key generation on the device (same Philox streams as the host twin)
+void keygen_sample(uint64_t* out, int E, int L, int n, const uint64_t* consts, uint64_t seed, uint32_t idx0, int mode,
+                   cudaStream_t st);
+void keygen_finish(const uint64_t* sk, uint64_t* pk, int E, int L, int n, const uint64_t* consts, uint64_t seed,
+                   uint32_t idx0, cudaStream_t st);
+void relin_message(uint64_t* evk, const uint64_t* s2, const int* limb_of, const uint64_t* w, int E, int L, int n,
+                   const uint64_t* consts, cudaStream_t st);
+
 // ---- second-generation persistent kernels (csrc/he/cuda/he_kernels2.cu) ----
 // tw2: [L][2][N][2] interleaved (w, w') tables (forward, inverse); pkx: [2][L][N][2] (pk, pk');
 // skx: [L][N][2] (s, s'); qbits: bit length of the largest prime. Each returns false (and

@@ -71,8 +71,14 @@ class BFVFracContext:
         return self
 
     # ---- keys ---------------------------------------------------------------------------
+    def _key_tables(self):
+        """Key generation runs where the context lives: CUDA kernels or the host twin (same keys for a seed)."""
+        if self.device.type == "cuda":
+            return self.tables, self.consts
+        return self._cpu["tables"], self._cpu["consts"]
+
     def keygen(self, seed: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
-        t, c = self._cpu["tables"], self._cpu["consts"]
+        t, c = self._key_tables()
         sk = self.ops.keygen_secret(1, self.logn, t, c, int(seed))
         pk = self.ops.keygen_public(sk, 1, self.logn, t, c, int(seed), 0)
         return sk.to(self.device), pk.to(self.device)
@@ -142,19 +148,16 @@ class BFVFracContext:
         ``size`` (how many powers of s SEAL 2.x could relinearise; 5 in the reference) is recorded: products here
         are relinearised immediately, so only the s^2 key is ever needed."""
         bit_count = max(1, min(int(bit_count), 60))
-        t, c = self._cpu["tables"], self._cpu["consts"]
-        sk_c = sk.cpu().contiguous()
-        s2 = torch.empty_like(sk_c)
-        self.ops.pointwise_(s2, sk_c, sk_c, 1, c, 2)
+        t, c = self._key_tables()
+        sk_d = sk.to(t.device).contiguous()
+        s2 = torch.empty_like(sk_d)
+        self.ops.pointwise_(s2, sk_d, sk_d, 1, c, 2)
         nd = (self.q.bit_length() + bit_count - 1) // bit_count
-        keys = []
-        for k in range(nd):
-            ek = self.ops.keygen_public(sk_c, 1, self.logn, t, c, int(seed), 1 + k)        # [2,1,N]
-            term = torch.empty_like(s2)
-            self.ops.pointwise_(term, s2, torch.tensor([pow(2, k * bit_count, self.q)], dtype=torch.int64), 1, c, 5)
-            self.ops.pointwise_(ek[0], ek[0], term, 1, c, 0)
-            keys.append(ek)
-        return BFVRelinKey(torch.stack(keys).to(self.device).contiguous(), bit_count, int(size))
+        w = [pow(2, k * bit_count, self.q) for k in range(nd)]
+        evk = self.ops.keygen_public_batch(sk_d, 1, self.logn, t, c, int(seed), 1, nd)          # [nd, 2, 1, N]
+        self.ops.relin_message_(evk, s2, torch.zeros(nd, dtype=torch.int32, device=t.device),
+                                torch.tensor(w, dtype=torch.int64, device=t.device), 1, c)
+        return BFVRelinKey(evk.to(self.device).contiguous(), bit_count, int(size))
 
     def _ext_basis(self):
         """Auxiliary RNS basis {q, p1, p2, p3}: wide enough (q * 2^174) to hold the integer tensor product of two

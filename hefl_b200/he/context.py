@@ -137,9 +137,16 @@ class CKKSContext:
         return q / 4.0
 
     # ------------------------------------------------------------------ keys
+    def _key_tables(self):
+        """(tables, consts) for key generation: the device copies on CUDA (kernels in he_kernels.cu), the host twin
+        otherwise. Both produce the same keys for a given seed."""
+        if self.device.type == "cuda":
+            return self.tables, self.consts
+        return self._cpu["tables"], self._cpu["consts"]
+
     def keygen(self, seed: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Returns (sk [L,N], pk [2,L,N]) on the context device (generated on the host)."""
-        t, c = self._cpu["tables"], self._cpu["consts"]
+        """Returns (sk [L,N], pk [2,L,N]) on the context device, generated there (HE.keyGen(), FLPyfhelin.py:340)."""
+        t, c = self._key_tables()
         sk = self.ops.keygen_secret(self.L, self.logn, t, c, int(seed))
         pk = self.ops.keygen_public(sk, self.L, self.logn, t, c, int(seed), 0)
         return sk.to(self.device), pk.to(self.device)
@@ -149,29 +156,27 @@ class CKKSContext:
 
         evk[i][k] = (-(a s + e) + 2^(k*digit_bits) * g_i * s^2, a) where g_i is the CRT basis
         element of limb i (1 mod q_i, 0 mod q_j): limb j of the message term is non-zero only
-        for j == i.
+        for j == i. All digits of all limbs are generated by one batched call (sample, NTT, finish) and one
+        message-term kernel, on the context device.
         """
-        t, c = self._cpu["tables"], self._cpu["consts"]
-        sk_c = sk.cpu()
-        s2 = torch.empty_like(sk_c)
-        self.ops.pointwise_(s2, sk_c, sk_c, self.L, c, 2)
-        keys = []
-        idx = 1
+        t, c = self._key_tables()
+        sk_d = sk.to(t.device).contiguous()
+        s2 = torch.empty_like(sk_d)
+        self.ops.pointwise_(s2, sk_d, sk_d, self.L, c, 2)
+        nd = [(self.primes[i].bit_length() + digit_bits - 1) // digit_bits for i in range(self.L)]
+        limb_of = [i for i in range(self.L) for _ in range(nd[i])]
+        w = [pow(2, k * digit_bits, self.primes[i]) for i in range(self.L) for k in range(nd[i])]
+        evk = self.ops.keygen_public_batch(sk_d, self.L, self.logn, t, c, int(seed), 1, len(w))
+        self.ops.relin_message_(evk, s2, torch.tensor(limb_of, dtype=torch.int32, device=t.device),
+                                torch.tensor(w, dtype=torch.int64, device=t.device), self.L, c)
+        evk = evk.to(self.device)
+        keys, first = [], 0
         for i in range(self.L):
-            nd = (self.primes[i].bit_length() + digit_bits - 1) // digit_bits
-            row = []
-            for k in range(nd):
-                ek = self.ops.keygen_public(sk_c, self.L, self.logn, t, c, int(seed), idx)
-                idx += 1
-                w = pow(2, k * digit_bits, self.primes[i])
-                scal = torch.zeros(self.L, dtype=torch.int64)
-                scal[i] = w
-                term = torch.empty_like(s2)
-                self.ops.pointwise_(term, s2, scal, self.L, c, 5)
-                self.ops.pointwise_(ek[0], ek[0], term, self.L, c, 0)
-                row.append(ek)
-            keys.append(torch.stack(row).to(self.device))
-        return RelinKey(keys, digit_bits)
+            keys.append(evk[first: first + nd[i]])
+            first += nd[i]
+        rlk = RelinKey(keys, digit_bits)
+        rlk._flat = (evk, nd, [sum(nd[:i]) for i in range(self.L)])
+        return rlk
 
     @staticmethod
     def _flat_evk(rlk: "RelinKey"):

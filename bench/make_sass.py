@@ -11,7 +11,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "hefl_b200", "_obj")
 OUT = os.path.join(ROOT, "profiles", "sass")
-KEY = re.compile(r"\b(UTCHMMA|UTCQMMA|UTCCP|UTMALDG|UTMASTG|UBLKCP|LDTM|STTM|UTCBAR|UTCATOMSWS|SYNCS|LDGMC|STGMC|REDGMC|MULTIMEM|ATOMG|ATOM|REDG|RED|LDGSTS|"
+KEY = re.compile(r"\b(LDSM|UTCHMMA|UTCQMMA|UTCCP|UTMALDG|UTMASTG|UBLKCP|LDTM|STTM|UTCBAR|UTCATOMSWS|SYNCS|LDGMC|STGMC|REDGMC|MULTIMEM|ATOMG|ATOM|REDG|RED|LDGSTS|"
                  r"HMMA|IMAD|LDS|STS|LDG|STG|SHFL|BAR|MEMBAR|ERRBAR|CCTL|ELECT|R2UR|UIADD3|UMOV|FFMA|FFMA2|FHFMA|UCGABAR_ARV|UCGABAR_WAIT|"
                  r"ACQBULK|DFMA|DADD|DMUL)\b")
 

@@ -170,3 +170,44 @@ def test_larger_presets(preset):
     ct = c.encrypt(vals, pk, seed=2)
     out = c.decrypt(ct, sk)
     assert (out - vals).abs().max() < 1e-6
+
+
+def test_evaluation_keys_satisfy_their_defining_equation(ctx):
+    """Every digit key of relin_keygen (one batched keygen call + the message-term kernel) must satisfy
+    b + a*s = e + 2^(k*w) * g_i * s^2 with a small error e: checked limb by limb against Python integers."""
+    from hefl_b200 import _ext
+
+    ops = _ext.ops()
+    sk, _ = ctx.keygen(seed=31)
+    rlk = ctx.relin_keygen(sk, seed=32, digit_bits=11)
+    t, c = ctx._cpu["tables"], ctx._cpu["consts"]
+    s2 = torch.empty_like(sk)
+    ops.pointwise_(s2, sk, sk, ctx.L, c, 2)
+    for i, keys in enumerate(rlk.keys):
+        assert keys.shape[0] == -(-ctx.primes[i].bit_length() // 11)
+        for k in range(keys.shape[0]):
+            b, a = keys[k, 0].clone(), keys[k, 1]
+            ops.pointwise_(b, a, sk, ctx.L, c, 3)                    # b + a*s (NTT domain)
+            ops.ntt_(b, t, c, ctx.L, ctx.logn, True)
+            s2c = s2.clone()
+            ops.ntt_(s2c, t, c, ctx.L, ctx.logn, True)
+            for l, q in enumerate(ctx.primes):
+                w = pow(2, k * 11, q) if l == i else 0
+                row = [int(v) for v in b[l, :64].tolist()]
+                ref = [int(v) for v in s2c[l, :64].tolist()]
+                for x, r in zip(row, ref):
+                    e = (x - w * r) % q
+                    e = e - q if e > q // 2 else e
+                    assert abs(e) <= 21, (i, k, l, e)               # centred binomial, 21 coin pairs
+
+
+def test_batched_public_keys_equal_one_call_per_index(ctx):
+    from hefl_b200 import _ext
+
+    ops = _ext.ops()
+    sk, _ = ctx.keygen(seed=33)
+    t, c = ctx._cpu["tables"], ctx._cpu["consts"]
+    batch = ops.keygen_public_batch(sk, ctx.L, ctx.logn, t, c, 34, 5, 3)
+    for e in range(3):
+        assert torch.equal(batch[e], ops.keygen_public(sk, ctx.L, ctx.logn, t, c, 34, 5 + e))
+    assert not torch.equal(batch[0], batch[1])

@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import torch
 from test_gpu_train import _setup
 
-mode = os.environ.get("HEFL_FWD_PAIR", "0")
+mode = os.environ.get("HEFL_FWD_PAIR", "1")
 out = []
 for seed in (5, 6, 7, 8):
     tr, pack, feed = _setup("tcgen05", "bf16", True, seed=seed)

@@ -512,7 +512,8 @@ void conv_dgrad(const void* dY, const void* Wd, void* dX, int B, int H, int W, i
 }
 
 // ------------------------------------------------------------------------------------------
-// G1b (opt-in, HEFL_FWD_PAIR): forward + pool with both columns of a pooling window in the SAME TMEM lane.
+// G1b (layer 1 by default, HEFL_FWD_PAIR=0 / all to change): forward + pool with both columns of a pooling window in
+// the SAME TMEM lane.
 // Validated against G1 on hardware (tests/test_gpu_conv.py::test_conv_fwd_pool_pair_matches_plain_kernel: same
 // pooled values and arg-max codes); 33.7 vs 40.4 us on layer 1 (B=32, 256x256), slower on the small layers.
 //
